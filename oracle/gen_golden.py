@@ -1,0 +1,124 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY -- golden-vector generator.
+
+Runs the reference's OWN, UNMODIFIED hot-path code (/root/reference/timing.py,
+retokenize.py, metrics.py) on CPU against the restated `whisper` dependency
+(oracle/whisper_shim) and writes inputs + outputs to tests/golden/*.npz.
+
+Run in the build container only (needs /root/reference):
+    python -m oracle.gen_golden
+The fixtures are committed; nothing at test/bench time reads /root/reference.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+from oracle import use_shim  # noqa: E402
+
+use_shim()
+sys.path.insert(0, REF)
+
+import retokenize as ref_retok  # noqa: E402  (the reference's own module)
+import timing as ref_timing  # noqa: E402  (the reference's own module)
+from whisper.audio import log_mel_spectrogram, pad_or_trim  # noqa: E402
+from whisper.tokenizer import get_tokenizer  # noqa: E402
+
+from oracle.synth import make_mel, make_model  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+CASES = [
+    # name, model, seed, gain, text, unit, aggr, topk, width, qk_scale, frames, extra
+    dict(name="micro_char_topk", model="micro", text="hello big world", unit="char", aggr="topk", topk=2, width=3, qk_scale=1.0, frames=97),
+    dict(name="micro_char_mean", model="micro", text="hello big world", unit="char", aggr="mean", topk=-1, width=7, qk_scale=1.0, frames=97),
+    dict(name="micro_sub_topk_all", model="micro", text="a quick brown fox jumps", unit="subword", aggr="topk", topk=50, width=5, qk_scale=0.5, frames=64),
+    dict(name="micro_width1", model="micro", text="no filter here", unit="char", aggr="topk", topk=3, width=1, qk_scale=1.0, frames=50),
+    dict(name="micro_short_frames", model="micro", text="hi yo", unit="char", aggr="topk", topk=2, width=7, qk_scale=1.0, frames=3),
+    dict(name="micro_coverage", model="micro", text="coverage penalty on", unit="char", aggr="topk", topk=2, width=3, qk_scale=1.0, frames=80, w_coverage=0.7, w_colnorm=0.5, w_rownorm=2.0),
+    dict(name="micro_eot_only", model="micro", text="", unit="char", aggr="topk", topk=2, width=3, qk_scale=1.0, frames=40),
+    dict(name="micro_full_ctx", model="micro", text="the whole context window is used for this one", unit="char", aggr="topk", topk=3, width=7, qk_scale=1.0, frames=256),
+    dict(name="mini_char_topk", model="mini", text="whisper has an internal word aligner", unit="char", aggr="topk", topk=5, width=3, qk_scale=1.0, frames=211),
+    dict(name="mini_sub_mean", model="mini", text="whisper has an internal word aligner", unit="subword", aggr="mean", topk=-1, width=7, qk_scale=1.0, frames=211),
+]
+
+
+def sphere_pcm(path):
+    """NIST SPHERE: ASCII header 'NIST_1A\\n   1024\\n', then int16 LE samples."""
+    raw = open(path, "rb").read()
+    assert raw[:7] == b"NIST_1A"
+    hdr = int(raw[8:16].split()[0])
+    return np.frombuffer(raw[hdr:], dtype="<i2").astype(np.float32) / 32768.0
+
+
+def run_case(c, model, tk, mel):
+    text_tokens = ref_retok.encode(c["text"], tk, c["unit"])
+    tokens = torch.tensor([*tk.sot_sequence, tk.no_timestamps, *text_tokens, tk.eot])
+    kw = {k: c[k] for k in ("w_colnorm", "w_rownorm", "w_coverage") if k in c}
+    w, logits = ref_timing.get_attentions(mel, tokens, model, tk, c["frames"], c["width"], c["qk_scale"])
+    res = ref_timing.force_align(w, text_tokens, tk, c["unit"], c["aggr"], c["topk"], **kw)
+    out = dict(
+        mel=mel.numpy(), tokens=tokens.numpy(), text_tokens=np.array(text_tokens, dtype=np.int64),
+        weights=w.numpy(), logits_digest=np.array([logits.double().sum().item(), logits.abs().double().sum().item()]),
+        sentinel=np.array(isinstance(res, list) and res[4] is None and len(res[0]) == 0 and c["text"] == ""),
+    )
+    if not out["sentinel"]:
+        words, st, en, matrix, scores = res
+        out.update(start_times=st, end_times=en, matrix=matrix.numpy(), words=np.array(json.dumps(words)))
+        if scores is not None:
+            out.update(score_values=np.array([s[0] for s in scores], dtype=np.float64),
+                       score_heads=np.array([s[1] for s in scores], dtype=np.int64))
+        # also pin the DTW path itself (what whisper.timing.dtw returns on -matrix)
+        from whisper.timing import dtw
+        ti, tj = dtw(-matrix)
+        out.update(path_text=ti.astype(np.int64), path_time=tj.astype(np.int64))
+    out["case"] = np.array(json.dumps(c))
+    return out
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    tk = get_tokenizer(True, language="English")
+    models = {}
+    for n, c in enumerate(CASES):
+        c = dict(c)
+        c.setdefault("seed", 0)
+        c.setdefault("gain", 4.0)
+        key = (c["model"], c["seed"], c["gain"])
+        if key not in models:
+            models[key] = make_model(c["model"], c["seed"], c["gain"])
+        model = models[key]
+        mel = make_mel(model.dims.n_mels, 2 * model.dims.n_audio_ctx, 2 * c["frames"], seed=100 + n)
+        out = run_case(c, model, tk, mel)
+        np.savez_compressed(os.path.join(OUT, c["name"] + ".npz"), **out)
+        print(c["name"], out["weights"].shape, "sentinel" if out["sentinel"] else (out["start_times"], out["end_times"]))
+
+    # C1: sample/test.wav (NIST SPHERE, 46592 samples -> 145 frames), Whisper-base dims,
+    # README.md:76-140 settings: char units, topk=10, medfilt_width=3.
+    pcm = sphere_pcm(os.path.join(REF, "sample", "test.wav"))
+    duration = len(pcm)
+    mel = log_mel_spectrogram(pad_or_trim(torch.from_numpy(pcm.copy())), 80)
+    c = dict(name="c1_base_sample", model="base", seed=0, gain=4.0, text="Artificial intelligence is for real",
+             unit="char", aggr="topk", topk=10, width=3, qk_scale=1.0, frames=duration // 320)
+    model = make_model("base", 0, 4.0)
+    out = run_case(c, model, tk, mel)
+    # keep the fixture small: only the speech part of the mel plus the constant pad value
+    n_keep = 2 * c["frames"] + 8
+    assert torch.all(mel[:, n_keep:] == mel[0, -1])
+    out["mel"] = mel[:, :n_keep].numpy()
+    out["mel_pad_value"] = np.array(mel[0, -1].item(), dtype=np.float32)
+    out["n_samples"] = np.array(duration)
+    np.savez_compressed(os.path.join(OUT, c["name"] + ".npz"), **out)
+    print(c["name"], out["weights"].shape, out["start_times"], out["end_times"])
+
+
+if __name__ == "__main__":
+    main()
