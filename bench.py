@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- utterances/sec of the alignment hot path (get_attentions + force_align).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo, one rank per GPU
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+Workload (BASELINE.json configs[1]): TIMIT-shaped synthetic utterances (2-4 s, ~40 chars),
+Whisper-medium dimensions with seeded random-init weights, char units, aggr=topk k=10,
+medfilt_width=3, fp32 like the reference (`whisper.load_model` default, allow_tf32 off).
+A step is one batch of `--batch` utterances through get_attentions_batch + force_align_batch;
+with N ranks every rank aligns its own batch (utterances are independent: weak scaling) and
+the job ends with the single all_gather of alignments and metric counters.
+
+Timed regions (CUDA events on the launching stream, barrier + synchronize on both sides,
+max over ranks):
+    value : mel and tokens already resident in HBM; ends with start/end times on the host
+    e2e   : mel and tokens start in pinned host memory; H2D copies inside the timed region
+One JSON line on rank 0; see the task contract for the keys.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "utterances/sec (Whisper-medium char align)"
+UNIT = "utt/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="medium")
+    ap.add_argument("--workload", default="timit", choices=["timit", "librispeech", "ami", "probe"])
+    ap.add_argument("--batch", type=int, default=16, help="utterances per step per GPU")
+    ap.add_argument("--topk", type=int, default=10)
+    ap.add_argument("--medfilt_width", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=2, help="utterances timed for cpu_baseline (0 = skip)")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"{args.workload}-shaped synthetic, Whisper-{args.model} dims (random-init, seeded), char units, "
+                    f"aggr=topk k={args.topk}, medfilt_width={args.medfilt_width}",
+        "utterances_per_step_per_gpu": args.batch,
+        "global_batch": args.batch * world,
+        "parallelism": f"utterance sharding x{world}, no data-path collective; one final all_gather",
+        "cache": "inputs larger than L2: each step streams the 3 GB fp32 weights and >1 GB of activations",
+    }
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        return False
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path
+# ------------------------------------------------------------------------------------------
+def cpu_reference_run(args, n_utts, warm):
+    """Times the reference's own algorithm (oracle port: fp32 torch on CPU with SDPA off,
+    unfold().sort() median, .item() scoring loop, C restatement of dtw_cpu) on `n_utts`
+    utterances of the same workload, all host threads.  Returns (utt/s, seconds, cores)."""
+    from dataclasses import asdict
+
+    from oracle import ref_path
+    from oracle.synth import make_dims  # noqa: F401
+    from oracle import use_shim
+
+    use_shim()
+    from whisper.model import ModelDimensions as ODims, Whisper as OWhisper
+
+    from whisper_char_alignment_b200 import synthetic, whisper_model
+    from whisper_char_alignment_b200.tokenizer import get_tokenizer
+
+    tk = get_tokenizer(True, language="English")
+    pm = whisper_model.load_model(args.model, None, seed=0, qk_gain=4.0)
+    om = OWhisper(ODims(**asdict(pm.dims)))
+    om.load_state_dict(pm.state_dict())
+    om.eval()
+    del pm
+    utts = synthetic.WORKLOADS[args.workload](n_utts + warm, tk, n_mels=om.dims.n_mels, seed=1234)
+
+    def one(u):
+        w, _ = ref_path.get_attentions(u.mel, u.tokens, om, tk, u.max_frames, args.medfilt_width, 1.0)
+        return ref_path.force_align(w, u.text_tokens, tk, "char" if args.workload != "ami" else "subword",
+                                    "topk", args.topk)
+
+    for u in utts[:warm]:
+        one(u)
+    t0 = time.perf_counter()
+    for u in utts[warm:]:
+        one(u)
+    dt = time.perf_counter() - t0
+    return n_utts / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    # a step of the reference arm is ONE utterance of the workload (bounded sample)
+    per_step = 1
+    ups, dt, cores = cpu_reference_run(args, args.steps * per_step, max(args.warmup, 1) * per_step)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": workload_config(args, 1) | {"utterances_per_step_per_gpu": per_step, "global_batch": per_step},
+        "cpu_baseline": {"value": ups, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} utterances of the workload, one per step, host CPU only"},
+        "e2e": {"value": ups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+
+    from whisper_char_alignment_b200 import _cabi, sharding, synthetic, timing, whisper_model
+    from whisper_char_alignment_b200.tokenizer import get_tokenizer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.backends.cuda.matmul.allow_tf32 = False  # fp32 like the reference's default model
+    torch.backends.cudnn.allow_tf32 = False
+    tk = get_tokenizer(True, language="English")
+    model = whisper_model.load_model(args.model, dev, seed=0, qk_gain=4.0)
+    dims = model.dims
+    unit = "subword" if args.workload == "ami" else "char"
+
+    # a pool of distinct batches per rank, cycled through the steps
+    n_batches = max(2, min(4, args.steps))
+    pool = synthetic.WORKLOADS[args.workload](args.batch * n_batches, tk, n_mels=dims.n_mels, seed=1000 + rank)
+    batches = [pool[i * args.batch: (i + 1) * args.batch] for i in range(n_batches)]
+    host = [(torch.stack([u.mel for u in b]).pin_memory(), [u.tokens.pin_memory() for u in b]) for b in batches]
+    resident = [(m.to(dev), [t.to(dev) for t in toks]) for m, toks in host]
+
+    def align(mels, toks, batch):
+        ws, _ = timing.get_attentions_batch(mels, toks, model, tk, [u.max_frames for u in batch],
+                                            args.medfilt_width, 1.0)
+        return timing.force_align_batch(ws, [u.text_tokens for u in batch], tk, unit, "topk", args.topk)
+
+    def step_resident(i):
+        mels, toks = resident[i % n_batches]
+        return align(mels, toks, batches[i % n_batches])
+
+    def step_e2e(i):
+        mels_h, toks_h = host[i % n_batches]
+        mels = mels_h.to(dev, non_blocking=True)
+        toks = [t.to(dev, non_blocking=True) for t in toks_h]
+        return align(mels, toks, batches[i % n_batches])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, collect=None):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        last = None
+        for i in range(steps):
+            last = step_fn(i)
+            if collect is not None:
+                collect(i, last)
+        if world > 1 and collect is not None:  # the job's single collective
+            collect(-1, None)
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, last
+
+    for i in range(args.warmup):
+        step_resident(i)
+    for i in range(min(args.warmup, 2)):
+        step_e2e(i)
+
+    local_alignments = {}
+
+    def collect(i, res):
+        if i < 0:
+            sharding.gather_alignments(local_alignments)
+            sharding.gather_counters(len(local_alignments), 0, 0)
+            return
+        for j, r in enumerate(res):
+            if not isinstance(r, list):
+                local_alignments[(i * args.batch + j) * world + rank] = (r[1], r[2])
+
+    launches0 = _cabi.launch_count()
+    with ClockSampler(local_rank) as clocks, _cabi.KernelTimer() as kt:
+        ms_value, last = timed(step_resident, args.steps, collect)
+    launches = _cabi.launch_count() - launches0
+    kernel_ms = kt.summary()
+    with ClockSampler(local_rank) as clocks_e2e:
+        ms_e2e, _ = timed(step_e2e, args.steps)
+
+    total_utts = args.batch * args.steps * world
+    value = total_utts / (ms_value / 1000.0)
+    e2e = total_utts / (ms_e2e / 1000.0)
+
+    # ---- bytes moved per step (counted from the tensors that are copied) -----------------
+    b0 = batches[0]
+    h2d = int(host[0][0].numel() * 4 + sum(t.numel() * 8 for t in host[0][1]))
+    d2h = 0
+    sot = len(tk.sot_sequence)
+    for u in b0:
+        n_rows = len(u.tokens) - sot - 1
+        d2h += n_rows * u.max_frames * 4 + 2 * 8 * (len(u.text.split()) + 1) + 2 * 4 * args.topk
+
+    # ---- roofline of the dominant kernel of OUR path: the capture launch --------------------
+    L, H, d = dims.n_text_layer, dims.n_text_head, dims.n_text_state
+    per_batch_bytes = []
+    dtw_cells = []
+    for b in batches:
+        t_max = max(len(u.tokens) for u in b)
+        per_batch_bytes.append(sum(4 * L * H * len(u.tokens) * u.max_frames for u in b)      # maps written once
+                               + sum(4 * L * (len(u.tokens) + u.max_frames) * d for u in b))  # Q, K[:F] read once
+        dtw_cells.append(sum((len(u.tokens) - sot - 1) * u.max_frames for u in b))
+        del t_max
+    used = [i % n_batches for i in range(args.steps)]
+    cap_calls, cap_ms = kernel_ms.get("wca_capture_attention", (0, 0.0))
+    cap_bytes = float(np.mean([per_batch_bytes[i] for i in used]))
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = cap_bytes / (cap_ms / max(cap_calls, 1) / 1000.0) / 1e9 if cap_ms > 0 else 0.0
+    dtw_calls, dtw_ms = kernel_ms.get("wca_dtw_align", (0, 0.0))
+    cells = float(np.mean([dtw_cells[i] for i in used]))
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and args.cpu_sample > 0:
+            ups, dt, cores = cpu_reference_run(args, args.cpu_sample, 1)
+            cpu = {"value": ups, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{args.cpu_sample} utterances of the same workload after 1 warm-up utterance, {dt:.1f} s"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic", "config": workload_config(args, world),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(), "clocks_e2e": clocks_e2e.summary(),
+            "roofline": {"kernel": "wca_capture_attention (QK^T capture + median filter + softmax)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": cap_bytes,
+                         "avg_launch_ms": cap_ms / max(cap_calls, 1)},
+            "cpu_baseline": cpu,
+            "stages_ms_per_step": {k: v[1] / args.steps for k, v in sorted(kernel_ms.items())},
+            "dtw_cells_per_s": cells / (dtw_ms / max(dtw_calls, 1) / 1000.0) if dtw_ms > 0 else None,
+            "utterances_aligned": len(local_alignments),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

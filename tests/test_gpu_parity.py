@@ -1,0 +1,306 @@
+"""GPU suite: the sm_100a kernels, called through the C ABI, against the oracle and the
+fixtures produced by the reference's own code.
+
+Bars (north_star): DTW paths / frame indices / word boundaries bit-exact given an identical
+cost matrix; attention maps within 1e-4 relative in fp32; head scores and aggregated
+matrices within 1e-5 relative (fp32 sums in a different order)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+MAP_RTOL = 1e-4  # north_star: attention maps within 1e-4 relative in fp32
+NAMES = golden_names()
+ALIGNED = [n for n in NAMES if "eot_only" not in n]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def timing():
+    from whisper_char_alignment_b200 import timing as t
+
+    return t
+
+
+def product_model(oracle_model, dev):
+    from dataclasses import asdict
+
+    from whisper_char_alignment_b200.whisper_model import ModelDimensions, Whisper
+
+    m = Whisper(ModelDimensions(**asdict(oracle_model.dims)))
+    m.load_state_dict(oracle_model.state_dict())
+    return m.eval().to(dev)
+
+
+# ------------------------------------------------------------------------ DTW
+def rand_cost(rng, n, m, kind):
+    x = rng.standard_normal((n, m)).astype(np.float32)
+    if kind == "ties":
+        x = np.round(x * 2) / 2
+    elif kind == "const":
+        x[:] = 0.25
+    elif kind == "neg_attn":  # what force_align feeds: minus a column-normalised map
+        x = -np.abs(x) / np.sqrt((x * x).sum(0, keepdims=True))
+    return x
+
+
+@pytest.mark.parametrize("kind", ["normal", "ties", "const", "neg_attn"])
+def test_dtw_bit_exact_vs_oracle_small_shapes(timing, dev, kind):
+    from oracle import dtw as odtw
+
+    rng = np.random.default_rng(11)
+    shapes = [(1, 1), (1, 7), (9, 1), (2, 2), (5, 3), (31, 33), (32, 32), (33, 31), (36, 145), (41, 150), (64, 17),
+              (65, 200), (100, 100), (17, 1500)]
+    costs = [rand_cost(rng, n, m, kind) for n, m in shapes]
+    got = timing.dtw_batch([torch.from_numpy(c).to(dev) for c in costs])
+    for c, (gi, gj) in zip(costs, got):
+        wi, wj = odtw.dtw_path(c)
+        np.testing.assert_array_equal(gi, wi)
+        np.testing.assert_array_equal(gj, wj)
+
+
+def test_dtw_bit_exact_full_size_and_properties(timing, dev):
+    """BASELINE.json config 3 sizes (N=401, M=1500) and the largest legal problem (445 x 1500)."""
+    from oracle import dtw as odtw
+
+    rng = np.random.default_rng(5)
+    for n, m in [(401, 1500), (445, 1500), (448, 1201)]:
+        c = rand_cost(rng, n, m, "neg_attn")
+        gi, gj = timing.dtw(torch.from_numpy(c).to(dev))
+        wi, wj = odtw.dtw_path(c)
+        np.testing.assert_array_equal(gi, wi)
+        np.testing.assert_array_equal(gj, wj)
+        # size-independent invariants of a DTW path
+        assert gi[0] == 0 and gj[0] == 0 and gi[-1] == n - 1 and gj[-1] == m - 1
+        di, dj = np.diff(gi), np.diff(gj)
+        assert ((di >= 0) & (dj >= 0) & (di + dj >= 1) & (di <= 1) & (dj <= 1)).all()
+        assert len(gi) <= n + m - 1 and (di > 0).sum() == n - 1
+
+
+def test_dtw_nonfinite_inputs_follow_the_cpu_rule(timing, dev):
+    """NaN compares false -> time step; +-inf propagate through fp32 adds exactly as on the CPU."""
+    from oracle import dtw as odtw
+
+    rng = np.random.default_rng(2)
+    cases = []
+    x = rng.standard_normal((6, 9)).astype(np.float32); x[2, 3] = np.nan; cases.append(x)
+    x = rng.standard_normal((6, 9)).astype(np.float32); x[:, 4] = np.inf; cases.append(x)
+    x = rng.standard_normal((4, 4)).astype(np.float32); x[1, 1] = -np.inf; cases.append(x)
+    x = np.full((3, 5), np.nan, np.float32); cases.append(x)
+    got = timing.dtw_batch([torch.from_numpy(c).to(dev) for c in cases])
+    for c, (gi, gj) in zip(cases, got):
+        wi, wj = odtw.dtw_path(c)
+        np.testing.assert_array_equal(gi, wi)
+        np.testing.assert_array_equal(gj, wj)
+
+
+@pytest.mark.parametrize("name", ALIGNED)
+def test_dtw_reproduces_reference_fixture_paths(name, timing, dev):
+    g = load_golden(name)
+    gi, gj = timing.dtw(torch.from_numpy(-g["matrix"]).to(dev))
+    np.testing.assert_array_equal(gi, g["path_text"])
+    np.testing.assert_array_equal(gj, g["path_time"])
+
+
+# ------------------------------------------------------ median filter + softmax
+@pytest.mark.parametrize("width", [1, 3, 5, 7, 9, 13, 31])
+def test_medfilt_softmax_matches_oracle(width, timing, dev):
+    from oracle import ref_path
+
+    g = torch.Generator().manual_seed(width)
+    for rows, n_ctx, frames, scale in [(7, 64, 64, 1.0), (40, 1500, 145, 1.0), (33, 1500, 1500, 0.5), (5, 40, 3, 1.0),
+                                       (3, 20, 1, 2.0), (16, 300, 257, 1.0)]:
+        x = torch.randn(rows, n_ctx, generator=g) * 4
+        want = ref_path.filtered_softmax(x, frames, width, scale)
+        got = timing.median_filter_softmax(x.to(dev), frames, width, scale).cpu()
+        torch.testing.assert_close(got, want, rtol=2e-6, atol=1e-12)
+        torch.testing.assert_close(got.sum(-1), torch.ones(rows), rtol=1e-5, atol=0)
+
+
+def test_medfilt_recovers_the_median_through_log_softmax(timing, dev):
+    """log p - max log p + max(median) must give back the median-filtered logits."""
+    from oracle import ref_path
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(12, 200, generator=g)
+    med = ref_path.median_along_frames(x, 7)
+    got = timing.median_filter_softmax(x.to(dev), 200, 7, 1.0).cpu()
+    recovered = got.log() - got.log().max(-1, keepdim=True)[0] + med.max(-1, keepdim=True)[0]
+    torch.testing.assert_close(recovered, med, rtol=0, atol=2e-5)
+
+
+# ------------------------------------------------------------- capture kernel
+def oracle_qk_inputs(model, mel, tokens):
+    """Q and K of every decoder cross-attention, taken on the CPU oracle model."""
+    qs, ks, handles = {}, {}, []
+    for i, blk in enumerate(model.decoder.blocks):
+        handles.append(blk.cross_attn.query.register_forward_hook(lambda m, a, o, i=i: qs.__setitem__(i, o)))
+        handles.append(blk.cross_attn.key.register_forward_hook(lambda m, a, o, i=i: ks.__setitem__(i, o)))
+    with torch.no_grad():
+        model(mel[None], tokens[None])
+    for h in handles:
+        h.remove()
+    n = len(model.decoder.blocks)
+    return [qs[i][0].contiguous() for i in range(n)], [ks[i][0].contiguous() for i in range(n)]
+
+
+@pytest.mark.parametrize("simt", [True, False], ids=["cuda_core", "default"])
+@pytest.mark.parametrize("name", ["micro_char_topk", "micro_full_ctx", "mini_char_topk", "micro_short_frames"])
+def test_capture_kernel_on_oracle_qk(name, simt, oracle_models, dev):
+    """Same Q/K bits in, so the only difference is the contraction itself."""
+    import numpy as np
+
+    from oracle import ref_path
+    from whisper_char_alignment_b200 import _cabi
+
+    g = load_golden(name)
+    c = g["case"]
+    model = oracle_models(c["model"], c.get("seed", 0), c.get("gain", 4.0))
+    mel, tokens = torch.from_numpy(g["mel"]), torch.from_numpy(g["tokens"])
+    q, k = oracle_qk_inputs(model, mel, tokens)
+    qk, _ = ref_path.capture_logits(model, mel, tokens)
+    L, H, T, F = model.dims.n_text_layer, model.dims.n_text_head, len(tokens), c["frames"]
+    recs = np.zeros(1, dtype=_cabi.UTT_DTYPE)
+    recs[0]["n_tokens"], recs[0]["n_frames"] = T, F
+    d_utts = _cabi.upload_utts(recs, dev)
+    qd, kd = [t.to(dev) for t in q], [t.to(dev) for t in k]
+    width = q[0].shape[-1]
+    base = _cabi.WCA_CAPTURE_FORCE_SIMT if simt else 0
+    raw = torch.empty(L * H * T * F, device=dev)
+    _cabi.capture_attention(qd, kd, H, width, width, d_utts, 1, T, F, c["width"], c["qk_scale"], raw,
+                            base | _cabi.WCA_CAPTURE_RAW_LOGITS)
+    want = qk[..., :F]
+    torch.testing.assert_close(raw.view(L, H, T, F).cpu(), want, rtol=1e-5, atol=2e-5 * want.abs().max().item())
+    ws = torch.empty(L * H * T * F, device=dev)
+    _cabi.capture_attention(qd, kd, H, width, width, d_utts, 1, T, F, c["width"], c["qk_scale"], ws, base)
+    torch.testing.assert_close(ws.view(L, H, T, F).cpu(), torch.from_numpy(g["weights"]), rtol=MAP_RTOL, atol=1e-9)
+
+
+# ------------------------------------------- scoring / top-k / aggregation / boundaries
+@pytest.mark.parametrize("name", NAMES)
+def test_force_align_on_reference_maps(name, timing, tokenizer, dev):
+    """Feed the reference's own maps: scores, selection, matrix, and the boundaries must agree;
+    the boundaries exactly (they are frame indices / 50)."""
+    g = load_golden(name)
+    c = g["case"]
+    kw = {k: c[k] for k in ("w_colnorm", "w_rownorm", "w_coverage") if k in c}
+    ws = torch.from_numpy(g["weights"]).to(dev)
+    res = timing.force_align(ws, g["text_tokens"].tolist(), tokenizer, c["unit"], c["aggr"], c["topk"], **kw)
+    if g["sentinel"]:
+        assert isinstance(res, list) and res == [[], [], [], [], None]
+        return
+    words, st, en, matrix, scores = res
+    assert words == g["words"]
+    assert matrix.device.type == "cpu" and matrix.dtype == torch.float32
+    np.testing.assert_allclose(matrix.numpy(), g["matrix"], rtol=1e-5, atol=1e-9)
+    if c["aggr"] == "topk":
+        assert [list(s[1]) for s in scores] == g["score_heads"].tolist()
+        np.testing.assert_allclose([s[0] for s in scores], g["score_values"], rtol=1e-5)
+        assert all(s[2] == f"sample_layer{s[1][0]}_head{s[1][1]}" for s in scores)
+    else:
+        assert scores is None
+    assert st.dtype == np.float64 and en.dtype == np.float64
+    np.testing.assert_array_equal(st, g["start_times"])
+    np.testing.assert_array_equal(en, g["end_times"])
+
+
+@pytest.mark.parametrize("name", ["micro_char_topk", "mini_char_topk", "micro_coverage"])
+def test_filter_attention_matches_oracle(name, timing, dev):
+    from oracle import ref_path
+
+    g = load_golden(name)
+    c = g["case"]
+    kw = {k: c[k] for k in ("w_colnorm", "w_rownorm", "w_coverage") if k in c}
+    w_cpu = torch.from_numpy(g["weights"])
+    for topk in (1, 3, 10 ** 6):
+        want_maps, want_scores = ref_path.filter_attention(w_cpu, topk, **kw)
+        got_maps, got_scores = timing.filter_attention(w_cpu.to(dev), topk, **kw)
+        assert [s[1] for s in got_scores] == [s[1] for s in want_scores]
+        assert [s[2] for s in got_scores] == [s[2] for s in want_scores]
+        np.testing.assert_allclose([s[0] for s in got_scores], [s[0] for s in want_scores], rtol=1e-5)
+        for a, b in zip(got_maps, want_maps):
+            assert a.shape == b.shape and torch.equal(a.cpu(), b)
+
+
+def test_probe_style_single_head_alignment(timing, tokenizer, dev):
+    """probe_oracle.py:89-90: force_align(w.unsqueeze(0), ..., aggregation='mean', topk=1) per head."""
+    from oracle import ref_path
+
+    g = load_golden("mini_char_topk")
+    w_cpu = torch.from_numpy(g["weights"])
+    toks = g["text_tokens"].tolist()
+    maps, _ = timing.filter_attention(w_cpu.to(dev), topk=360)
+    ref_maps, _ = ref_path.filter_attention(w_cpu, topk=360)
+    batch = timing.force_align_batch([m.unsqueeze(0) for m in maps], [toks] * len(maps), tokenizer, "char", "mean", 1)
+    for got, rm in zip(batch, ref_maps):
+        want = ref_path.force_align(rm.unsqueeze(0), toks, tokenizer, "char", "mean", 1)
+        np.testing.assert_allclose(got[3].numpy(), want[3].numpy(), rtol=1e-5)
+        # boundaries from the device matrix through the oracle DTW == device boundaries (bit-exact stage)
+        from oracle import dtw as odtw
+
+        ti, tj = odtw.dtw_path(-got[3].numpy())
+        _, wt = ref_path.split_tokens_on_spaces(toks + [tokenizer.eot], tokenizer, "char")
+        st, en, _ = ref_path.boundaries_from_path(ti, tj, wt)
+        np.testing.assert_array_equal(got[1], st)
+        np.testing.assert_array_equal(got[2], en)
+
+
+# ------------------------------------------------------------------ end to end
+@pytest.mark.parametrize("name", NAMES)
+def test_end_to_end_against_reference_fixture(name, timing, tokenizer, oracle_models, dev):
+    """Model forward on cuBLAS + every kernel, against what the reference produced on CPU.
+    fp32 GEMMs in another summation order move the maps by ~1e-5 relative; the stated bound
+    for the whole network is 1e-3 (the kernel-only bound is MAP_RTOL, tested above)."""
+    g = load_golden(name)
+    c = g["case"]
+    model = product_model(oracle_models(c["model"], c.get("seed", 0), c.get("gain", 4.0)), dev)
+    mel = torch.from_numpy(g["mel"]).to(dev)
+    tokens = torch.from_numpy(g["tokens"]).to(dev)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        w, logits = timing.get_attentions(mel, tokens, model, tokenizer, c["frames"], c["width"], c["qk_scale"])
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert w.shape == g["weights"].shape and w.dtype == torch.float32 and w.is_cuda
+    assert logits.shape == (len(g["tokens"]), model.dims.n_vocab)
+    torch.testing.assert_close(w.cpu(), torch.from_numpy(g["weights"]), rtol=1e-3, atol=1e-7)
+    kw = {k: c[k] for k in ("w_colnorm", "w_rownorm", "w_coverage") if k in c}
+    res = timing.force_align(w, g["text_tokens"].tolist(), tokenizer, c["unit"], c["aggr"], c["topk"], **kw)
+    if g["sentinel"]:
+        assert res == [[], [], [], [], None]
+        return
+    words, st, en, matrix, scores = res
+    assert words == g["words"]
+    np.testing.assert_allclose(matrix.numpy(), g["matrix"], rtol=1e-3, atol=1e-7)
+    # word boundaries agree to the frame
+    np.testing.assert_array_equal(np.round(st * 50).astype(int), np.round(g["start_times"] * 50).astype(int))
+    np.testing.assert_array_equal(np.round(en * 50).astype(int), np.round(g["end_times"] * 50).astype(int))
+
+
+def test_batched_path_equals_single_utterance_path(timing, tokenizer, oracle_models, dev):
+    names = ["micro_char_topk", "micro_width1", "micro_full_ctx", "micro_coverage"]
+    gs = [load_golden(n) for n in names]
+    model = product_model(oracle_models("micro"), dev)
+    mels = torch.stack([torch.from_numpy(g["mel"]) for g in gs]).to(dev)
+    toks = [torch.from_numpy(g["tokens"]).to(dev) for g in gs]
+    frames = [g["case"]["frames"] for g in gs]
+    wb, _ = timing.get_attentions_batch(mels, toks, model, tokenizer, frames, 3, 1.0)
+    singles = [timing.get_attentions(mels[i], toks[i], model, tokenizer, frames[i], 3, 1.0)[0] for i in range(len(gs))]
+    for a, b in zip(wb, singles):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-9)
+    text = [g["text_tokens"].tolist() for g in gs]
+    rb = timing.force_align_batch(wb, text, tokenizer, "char", "topk", 2)
+    for i, r in enumerate(rb):
+        one = timing.force_align(wb[i], text[i], tokenizer, "char", "topk", 2)
+        assert r[0] == one[0] and r[4] == one[4]
+        np.testing.assert_array_equal(r[1], one[1])
+        np.testing.assert_array_equal(r[2], one[2])
+        assert torch.equal(r[3], one[3])

@@ -1,0 +1,151 @@
+"""CPU suite, part 2: host-side logic of the product (tokenisation, word grouping, metrics,
+argument conventions) and the C-ABI surface (library loads, exports every declared symbol,
+descriptor layout agrees with the header).  No kernel is launched here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import ref_path
+from whisper_char_alignment_b200 import _cabi, metrics, retokenize
+from whisper_char_alignment_b200.tokenizer import get_tokenizer
+
+TEXTS = ["Artificial intelligence is for real", "hello  big   world ", "a", "", "don't stop, it's 7 o'clock",
+         "naïve café déjà vu", "x y z"]
+
+
+@pytest.mark.parametrize("unit", ["char", "subword"])
+@pytest.mark.parametrize("text", TEXTS)
+def test_encode_and_word_split_match_the_restated_reference(text, unit, tokenizer):
+    ids = retokenize.encode(text, tokenizer, unit)
+    assert ids == ref_path.encode(text, tokenizer, unit)
+    got = retokenize.split_tokens_on_spaces(ids + [tokenizer.eot], tokenizer, unit)
+    want = ref_path.split_tokens_on_spaces(ids + [tokenizer.eot], tokenizer, unit)
+    assert got == want
+    assert got[0][-1] == "<|endoftext|>"
+    assert sum(len(t) for t in got[1]) == len(ids) + 1
+    if unit == "char":
+        assert tokenizer.decode(ids) == " ".join(text.split())
+    else:
+        assert tokenizer.decode(ids) == text
+
+
+def test_tokenizer_matches_oracle_shim_tokenizer():
+    from oracle import use_shim
+
+    use_shim()
+    from whisper.tokenizer import get_tokenizer as shim_get
+
+    a, b = get_tokenizer(True, language="English"), shim_get(True, language="English")
+    assert (a.sot_sequence, a.eot, a.no_timestamps) == (b.sot_sequence, b.eot, b.no_timestamps)
+    for text in TEXTS:
+        assert a.encode(text) == b.encode(text)
+        ids = a.encode(text) + [a.eot]
+        assert a.split_to_word_tokens(ids) == b.split_to_word_tokens(ids)
+        assert a.split_tokens_on_unicode(ids) == b.split_tokens_on_unicode(ids)
+    en = get_tokenizer(False)
+    assert len(en.sot_sequence) == 1 and en.eot == 50256
+
+
+def test_unit_assertion_mirrors_reference():
+    tk = get_tokenizer(True)
+    with pytest.raises(AssertionError):
+        retokenize.encode("a", tk, "phone")
+    with pytest.raises(AssertionError):
+        retokenize.split_tokens_on_spaces([1, 2], tk, "word")
+
+
+def test_remove_punctuation():
+    assert retokenize.remove_punctuation("Hello, world! It's 42.") == "Hello world It's fortytwo"  # the final pass strips the hyphen, as in the reference
+    assert retokenize.remove_punctuation("...") == ""
+
+
+def test_metrics_known_answers():
+    assert metrics.eval_n1([0.5, 1.0, 2.0], [0.51, 1.5, 2.01], 0.02) == (2, 2)
+    assert metrics.eval_n1([0.5], [], 0.02) == (0, 0)
+    tp, fp, fn = metrics.eval_n1_strict([0.5, 1.0], [0.5, 1.0, 1.4], ["Hi,", "there"], ["hi", "THERE", "x"], 0.02)
+    assert (tp, fp, fn) == (2, 1, 0)
+    p, r, f1, rval, os_ = metrics.get_seg_metrics(8, 8, 10, 16)
+    assert abs(p - 0.8) < 1e-6 and abs(r - 0.5) < 1e-6 and abs(f1 - 2 * 0.4 / 1.3) < 1e-6
+    a = torch.tensor([[0.2, 0.9, 0.0], [0.1, 0.3, 0.0]])
+    torch.testing.assert_close(metrics.coverage_penalty(a), ref_path.coverage_penalty(a))
+    assert abs(metrics.coverage_penalty(a).item() - (0.5 + 1.2 + 0.5 - 1.5)) < 1e-6
+
+
+# ------------------------------------------------------------------ C-ABI surface
+HEADER = os.path.join(ROOT, "include", "wca_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"WCA_API\s+[\w\s\*]+?\b(wca_\w+)\s*\(", src)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from whisper_char_alignment_b200 import build
+
+    build.build()
+    lib = _cabi.load()
+    names = declared_symbols()
+    assert len(names) >= 10
+    assert sorted(_cabi.EXPORTS) == names
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.wca_abi_version() == 1
+    assert lib.wca_dtw_workspace_bytes(4, 445, 1500) == 0  # largest legal Whisper problem fits in smem
+    assert lib.wca_dtw_workspace_bytes(2, 1000, 4000) > 0
+
+
+def test_descriptor_layout_matches_header(tmp_path):
+    prog = tmp_path / "layout.c"
+    fields = [name for name, _ in _cabi.UttDesc._fields_]
+    body = "\n".join(f'    printf("{f} %zu\\n", offsetof(wca_utt_t, {f}));' for f in fields)
+    prog.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "wca_b200.h"\n'
+        'int main(void) {\n    printf("size %zu\\n", sizeof(wca_utt_t));\n' + body + "\n    return 0;\n}\n"
+    )
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
+    lines = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    assert int(lines["size"]) == ctypes.sizeof(_cabi.UttDesc) == _cabi.UTT_DTYPE.itemsize
+    for f in fields:
+        assert int(lines[f]) == getattr(_cabi.UttDesc, f).offset == _cabi.UTT_DTYPE.fields[f][1], f
+
+
+def test_product_refuses_cpu_tensors_instead_of_falling_back(tokenizer):
+    from whisper_char_alignment_b200 import timing
+
+    w = torch.rand(2, 2, 8, 16)
+    with pytest.raises(_cabi.WcaError):
+        timing.force_align(w, [104, 105], tokenizer, "char", "mean")
+    with pytest.raises(_cabi.WcaError):
+        timing.dtw(torch.rand(4, 5))
+    with pytest.raises(_cabi.WcaError):
+        timing.median_filter_softmax(torch.rand(3, 20), 10)
+
+
+def test_force_align_argument_errors_mirror_reference(tokenizer):
+    from whisper_char_alignment_b200 import timing
+
+    w = torch.rand(2, 2, 8, 16)
+    with pytest.raises(AssertionError):  # timing.py:92
+        timing.force_align(w, [104], tokenizer, "char", "topk", topk=-1)
+    with pytest.raises(UnboundLocalError):  # timing.py:102 with an unknown aggregation
+        timing.force_align(w, [104], tokenizer, "char", "median")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "whisper_char_alignment_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+    code = "import sys; import whisper_char_alignment_b200; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
+    subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)

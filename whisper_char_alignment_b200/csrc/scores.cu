@@ -1,0 +1,170 @@
+// Head scoring, top-k selection and aggregation (north-star kernel 3).
+// Replaces the reference's filter_attention (timing.py:13-43, a Python loop with one
+// blocking .item() per head), coverage_penalty (metrics.py:99-111) and the aggregation
+// branches of force_align (timing.py:84-97).  Everything stays on the device: scores ->
+// ranks -> selected list -> (N, F) matrix, no host round trip in between.
+#include "common.cuh"
+
+namespace wca {
+
+// Deterministic block sum (fixed shuffle tree + fixed warp order); result valid on thread 0.
+__device__ __forceinline__ float block_sum_256(float v, float *scratch /* >= 8 floats */) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    float total = 0.f;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) total += scratch[w];
+    return total;
+}
+
+// grid (n_heads, n_utts), block 256.  HBM: the (T, F) tile is read once from DRAM (the
+// column pass re-reads it through L2).
+__global__ void __launch_bounds__(256) head_scores_kernel(const float *__restrict__ ws,
+                                                          const wca_utt_t *__restrict__ utts, float w_col,
+                                                          float w_row, float w_cov, float *__restrict__ scores) {
+    __shared__ float scratch[8];
+    const wca_utt_t u = utts[blockIdx.y];
+    const int T = u.n_tokens, F = u.n_frames;
+    const float *a = ws + u.ws_off + (int64_t)blockIdx.x * T * F;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+
+    float row_part = 0.f;  // sum_t ||a[t,:]||_2        (timing.py:24)
+    if (w_row > 0.f) {
+        for (int t = warp; t < T; t += warps) {
+            const float *r = a + (int64_t)t * F;
+            float ss = 0.f;
+            for (int f = lane; f < F; f += kWarp) {
+                const float p = r[f];
+                ss = fmaf(p, p, ss);
+            }
+            ss = warp_sum(ss);
+            if (lane == 0) row_part += sqrtf(ss);
+        }
+    }
+    float col_part = 0.f;  // sum_f ||a[:,f]||_2        (timing.py:21)
+    float cov_part = 0.f;  // sum_f max(sum_t a[t,f], .5) (metrics.py:104-109)
+    if (w_col > 0.f || w_cov > 0.f) {
+        for (int f = threadIdx.x; f < F; f += blockDim.x) {
+            float ss = 0.f, s = 0.f;
+            for (int t = 0; t < T; ++t) {
+                const float p = a[(int64_t)t * F + f];
+                ss = fmaf(p, p, ss);
+                s += p;
+            }
+            col_part += sqrtf(ss);
+            cov_part += fmaxf(s, 0.5f);
+        }
+    }
+    const float row_sum = block_sum_256(row_part, scratch);
+    const float col_sum = block_sum_256(col_part, scratch);
+    const float cov_sum = block_sum_256(cov_part, scratch);
+    if (threadIdx.x == 0) {
+        float score = 0.f;
+        if (w_col > 0.f) score += w_col * col_sum;
+        if (w_row > 0.f) score += w_row * row_sum;
+        if (w_cov > 0.f) score -= w_cov * (cov_sum - (float)F * 0.5f);
+        scores[u.score_off + blockIdx.x] = score;
+    }
+}
+
+// grid (n_utts), block 256, dynamic smem n_heads floats.  Rank by counting with the
+// reference's tuple order (score, layer, head): ties go to the smaller head index.
+__global__ void __launch_bounds__(256) topk_heads_kernel(const float *__restrict__ scores,
+                                                         const wca_utt_t *__restrict__ utts, int n_heads,
+                                                         int32_t *__restrict__ sel, float *__restrict__ sel_scores) {
+    extern __shared__ float s_sc[];
+    const wca_utt_t u = utts[blockIdx.x];
+    for (int i = threadIdx.x; i < n_heads; i += blockDim.x) s_sc[i] = scores[u.score_off + i];
+    __syncthreads();
+    const int n_sel = u.n_sel < n_heads ? u.n_sel : n_heads;
+    const int first = n_heads - n_sel;
+    for (int i = threadIdx.x; i < n_heads; i += blockDim.x) {
+        const float si = s_sc[i];
+        int rank = 0;
+        for (int j = 0; j < n_heads; ++j) {
+            const float sj = s_sc[j];
+            rank += (sj < si) || (sj == si && j < i);
+        }
+        if (rank >= first) {
+            sel[u.sel_off + rank - first] = i;
+            if (sel_scores) sel_scores[u.sel_off + rank - first] = si;
+        }
+    }
+}
+
+// grid (ceil(max_frames/32), n_utts), block 256 = 8 warps x 32 columns, dynamic smem
+// T*32 floats of accumulators.  Lane <-> frame (128-byte coalesced rows), warp <-> rows.
+__global__ void __launch_bounds__(256) aggregate_heads_kernel(const float *__restrict__ ws,
+                                                              const int32_t *__restrict__ sel,
+                                                              const wca_utt_t *__restrict__ utts,
+                                                              float *__restrict__ matrix) {
+    extern __shared__ float acc_s[];  // [T][32]
+    __shared__ float part[2][8][kWarp];
+    const wca_utt_t u = utts[blockIdx.y];
+    const int T = u.n_tokens, F = u.n_frames;
+    const int f0 = blockIdx.x * kWarp;
+    if (f0 >= F) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    const int f = f0 + lane;
+    const bool live = f < F;
+
+    for (int t = warp; t < T; t += warps) acc_s[t * kWarp + lane] = 0.f;
+
+    for (int i = 0; i < u.n_sel; ++i) {
+        const float *a = ws + u.ws_off + (int64_t)sel[u.sel_off + i] * T * F;
+        float ss = 0.f;
+        if (live)
+            for (int t = warp; t < T; t += warps) {
+                const float p = a[(int64_t)t * F + f];
+                ss = fmaf(p, p, ss);
+            }
+        part[i & 1][warp][lane] = ss;
+        __syncthreads();
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += (w < warps) ? part[i & 1][w][lane] : 0.f;
+        const float cn = sqrtf(tot);  // ||a_i[:, f]||_2 over all T rows (timing.py:86 / :96)
+        if (live)
+            for (int t = warp; t < T; t += warps) acc_s[t * kWarp + lane] += a[(int64_t)t * F + f] / cn;
+    }
+
+    const float count = (float)u.n_sel;  // torch.mean = sum / count
+    if (live)
+        for (int t = u.row_begin + warp; t < u.row_end; t += warps)
+            matrix[u.matrix_off + (int64_t)(t - u.row_begin) * F + f] = acc_s[t * kWarp + lane] / count;
+}
+
+int launch_head_scores(const float *d_ws, const wca_utt_t *d_utts, int n_utts, int n_heads, float w_col,
+                       float w_row, float w_cov, float *d_scores, cudaStream_t stream) {
+    head_scores_kernel<<<dim3(n_heads, n_utts), 256, 0, stream>>>(d_ws, d_utts, w_col, w_row, w_cov, d_scores);
+    WCA_LAUNCH_CHECK("head_scores_kernel");
+    return WCA_OK;
+}
+
+int launch_topk_heads(const float *d_scores, const wca_utt_t *d_utts, int n_utts, int n_heads, int32_t *d_sel,
+                      float *d_sel_scores, cudaStream_t stream) {
+    topk_heads_kernel<<<n_utts, 256, n_heads * sizeof(float), stream>>>(d_scores, d_utts, n_heads, d_sel,
+                                                                         d_sel_scores);
+    WCA_LAUNCH_CHECK("topk_heads_kernel");
+    return WCA_OK;
+}
+
+int launch_aggregate_heads(const float *d_ws, const int32_t *d_sel, const wca_utt_t *d_utts, int n_utts,
+                           int max_tokens, int max_frames, float *d_matrix, cudaStream_t stream) {
+    const size_t smem = (size_t)max_tokens * kWarp * sizeof(float);
+    if (smem > 200u * 1024u) {
+        set_error("wca_aggregate_heads: max_tokens=%d exceeds the shared-memory accumulator", max_tokens);
+        return WCA_ERR_UNSUPPORTED;
+    }
+    if (smem > 48u * 1024u)
+        WCA_CUDA(cudaFuncSetAttribute(aggregate_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const dim3 grid((max_frames + kWarp - 1) / kWarp, n_utts);
+    aggregate_heads_kernel<<<grid, 256, smem, stream>>>(d_ws, d_sel, d_utts, d_matrix);
+    WCA_LAUNCH_CHECK("aggregate_heads_kernel");
+    return WCA_OK;
+}
+
+}  // namespace wca

@@ -1,0 +1,385 @@
+"""B200-native `timing` module: same entry points, arguments, return conventions and
+error behaviour as the reference's timing.py, with the arithmetic on sm_100a kernels.
+
+    get_attentions(mel, tokens, model, tokenizer, max_frames, medfilt_width=7, qk_scale=1.0)
+        reference timing.py:45-67
+    filter_attention(attns, topk=20, w_colnorm=1, w_rownorm=1, w_coverage=0)
+        reference timing.py:13-43
+    force_align(ws, tokens, tokenizer, aligned_unit_type='subword', aggregation="mean", topk=-1,
+                w_colnorm=1.0, w_rownorm=1.0, w_coverage=0.0)
+        reference timing.py:69-114
+
+plus `*_batch` variants that push many utterances through one launch of each kernel
+(the reference is strictly one utterance at a time, infer_ali.py:48,57).
+
+How it differs underneath (results identical):
+  * the model runs with SDPA on; instead of hooking `cross_attn` for a materialised
+    (1,H,T,1500) `qk`, the outputs of `cross_attn.query` / `cross_attn.key` are tapped and
+    the capture kernel writes the trimmed, filtered, soft-maxed (L,H,T,F) maps directly;
+  * head scoring, top-k, aggregation, DTW, backtrace and boundary extraction run
+    back-to-back on the device; one device->host copy at the end replaces the reference's
+    L*H `.item()` syncs and the `.cpu()` before DTW.
+
+There is no CPU path here: tensors must be CUDA tensors and the extension must be built.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .retokenize import split_tokens_on_spaces
+
+TOKENS_PER_SECOND = 50  # whisper.audio: SAMPLE_RATE // (HOP_LENGTH * 2)
+
+__all__ = [
+    "get_attentions", "get_attentions_batch", "filter_attention", "force_align", "force_align_batch",
+    "dtw", "dtw_batch", "median_filter_softmax",
+]
+
+
+# ---------------------------------------------------------------------------------
+# get_attentions
+# ---------------------------------------------------------------------------------
+class _CrossAttentionTap:
+    """Forward hooks on every decoder block's cross_attn.query / cross_attn.key."""
+
+    def __init__(self, model):
+        self.blocks = list(model.decoder.blocks)
+        self.q = [None] * len(self.blocks)
+        self.k = [None] * len(self.blocks)
+        self._handles = []
+
+    def __enter__(self):
+        for idx, blk in enumerate(self.blocks):
+            ca = blk.cross_attn
+            self._handles.append(ca.query.register_forward_hook(lambda _m, _i, out, idx=idx: self.q.__setitem__(idx, out)))
+            self._handles.append(ca.key.register_forward_hook(lambda _m, _i, out, idx=idx: self.k.__setitem__(idx, out)))
+        return self
+
+    def __exit__(self, *exc):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+        return False
+
+
+def _as_f32_rows(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def get_attentions_batch(mels, tokens_list: Sequence[torch.Tensor], model, tokenizer, max_frames_list,
+                         medfilt_width: int = 7, qk_scale: float = 1.0, *, raw_logits: bool = False,
+                         force_simt: bool = False):
+    """Batched get_attentions.  mels: (B, n_mels, n_frames_in) tensor or list of (n_mels, n_frames_in);
+    tokens_list: B 1-D int64 tensors; max_frames_list: B ints.
+    Returns ([weights_b (L,H,T_b,F_b) fp32], [logits_b (T_b, V) fp32])."""
+    if isinstance(mels, (list, tuple)):
+        mels = torch.stack(list(mels))
+    B = mels.shape[0]
+    device = mels.device
+    if device.type != "cuda":
+        raise _cabi.WcaError("get_attentions: tensors must be on a CUDA device (no CPU fallback exists)")
+    n_layers = model.dims.n_text_layer
+    n_heads = model.dims.n_text_head
+    n_ctx = model.dims.n_audio_ctx
+    lens = [int(t.shape[0]) for t in tokens_list]
+    frames = [int(f) for f in max_frames_list]
+    if len(lens) != B or len(frames) != B:
+        raise ValueError("mels, tokens and max_frames must have the same batch length")
+    for f in frames:
+        if not 1 <= f <= n_ctx:
+            raise ValueError(f"max_frames={f} outside [1, {n_ctx}]")
+    t_max = max(lens)
+    # right-pad with each sequence's own last token: causal masking hides the padding
+    tok = torch.stack([
+        torch.cat([t.to(device), t[-1:].to(device).expand(t_max - t.shape[0])]) if t.shape[0] < t_max else t.to(device)
+        for t in tokens_list
+    ])
+
+    with torch.no_grad(), _CrossAttentionTap(model) as tap:
+        out_logits = model(mels, tok)
+    q_layers = [_as_f32_rows(q) for q in tap.q]
+    k_layers = [_as_f32_rows(k) for k in tap.k]
+    width = q_layers[0].shape[-1]
+
+    recs = np.zeros(B, dtype=_cabi.UTT_DTYPE)
+    off = 0
+    for b in range(B):
+        recs[b]["n_tokens"], recs[b]["n_frames"] = lens[b], frames[b]
+        recs[b]["q_row0"], recs[b]["k_row0"] = b * t_max, b * k_layers[0].shape[1]
+        recs[b]["ws_off"] = off
+        off += n_layers * n_heads * lens[b] * frames[b]
+    d_utts = _cabi.upload_utts(recs, device)
+    ws = torch.empty(off, dtype=torch.float32, device=device)
+    flags = (_cabi.WCA_CAPTURE_RAW_LOGITS if raw_logits else 0) | (_cabi.WCA_CAPTURE_FORCE_SIMT if force_simt else 0)
+    _cabi.capture_attention(q_layers, k_layers, n_heads, width, width, d_utts, B, t_max, max(frames),
+                            int(medfilt_width), float(qk_scale), ws, flags)
+    weights, logits = [], []
+    for b in range(B):
+        n = n_layers * n_heads * lens[b] * frames[b]
+        weights.append(ws[recs[b]["ws_off"]: recs[b]["ws_off"] + n].view(n_layers, n_heads, lens[b], frames[b]))
+        logits.append(out_logits[b, : lens[b]])
+    return weights, logits
+
+
+def get_attentions(mel, tokens, model, tokenizer, max_frames, medfilt_width=7, qk_scale=1.0):
+    """Drop-in for reference timing.py:45-67.  `tokenizer` is accepted and unused, as there."""
+    weights, logits = get_attentions_batch(mel.unsqueeze(0), [tokens], model, tokenizer, [int(max_frames)],
+                                           medfilt_width, qk_scale)
+    return weights[0], logits[0]
+
+
+def median_filter_softmax(logits: torch.Tensor, max_frames: int, medfilt_width: int = 7, qk_scale: float = 1.0):
+    """timing.py:64-66 on already materialised logits (..., n_ctx): trim, median filter,
+    scale, softmax.  For callers that captured `qk` themselves (e.g. a stock upstream hook)."""
+    if logits.device.type != "cuda":
+        raise _cabi.WcaError("median_filter_softmax: CUDA tensor required")
+    x = _as_f32_rows(logits)
+    ld = x.shape[-1]
+    rows = x.numel() // ld
+    out = torch.empty(*x.shape[:-1], int(max_frames), dtype=torch.float32, device=x.device)
+    _cabi.medfilt_softmax(x, rows, ld, int(max_frames), int(medfilt_width), float(qk_scale), out)
+    return out
+
+
+# ---------------------------------------------------------------------------------
+# device-side plan shared by filter_attention / force_align
+# ---------------------------------------------------------------------------------
+class _Plan:
+    """Offsets of one batch inside the flat work buffers + the uploaded descriptors."""
+
+    def __init__(self, ws_list, row_begin, n_sel_list, word_counts=None):
+        self.B = len(ws_list)
+        self.device = ws_list[0].device
+        self.base_ptr = ws_list[0].data_ptr()
+        recs = np.zeros(self.B, dtype=_cabi.UTT_DTYPE)
+        score_off = sel_off = matrix_off = path_off = jump_off = word_off = 0
+        self.n_heads = None
+        for b, w in enumerate(ws_list):
+            if w.device != self.device or w.dtype != torch.float32 or not w.is_contiguous():
+                raise _cabi.WcaError("attention maps must be contiguous fp32 CUDA tensors on one device")
+            heads = w.shape[0] * w.shape[1]
+            if self.n_heads is None:
+                self.n_heads = heads
+            elif heads != self.n_heads:
+                raise ValueError("all utterances of a batch must have the same number of heads")
+            T, F = int(w.shape[2]), int(w.shape[3])
+            delta = w.data_ptr() - self.base_ptr
+            assert delta % 4 == 0
+            r = recs[b]
+            r["n_tokens"], r["n_frames"] = T, F
+            r["row_begin"], r["row_end"] = row_begin, max(T - 1, row_begin)
+            r["n_sel"] = n_sel_list[b]
+            r["n_words"] = 0 if word_counts is None else word_counts[b]
+            r["ws_off"] = delta // 4
+            r["score_off"], r["sel_off"], r["matrix_off"] = score_off, sel_off, matrix_off
+            r["path_off"], r["jump_off"], r["word_off"] = path_off, jump_off, word_off
+            n_rows = int(r["row_end"] - r["row_begin"])
+            score_off += heads
+            sel_off += int(r["n_sel"])
+            matrix_off += n_rows * F
+            path_off += n_rows + F
+            jump_off += n_rows
+            word_off += int(r["n_words"]) + 1
+        self.recs = recs
+        self.totals = dict(score=score_off, sel=sel_off, matrix=matrix_off, path=path_off, jump=jump_off, word=word_off)
+        self.max_tokens = int(recs["n_tokens"].max())
+        self.max_frames = int(recs["n_frames"].max())
+        self.max_rows = int((recs["row_end"] - recs["row_begin"]).max())
+        self.d_utts = _cabi.upload_utts(recs, self.device)
+
+
+def _score_and_select(plan: _Plan, w_colnorm, w_rownorm, w_coverage):
+    dev = plan.device
+    scores = torch.empty(plan.totals["score"], dtype=torch.float32, device=dev)
+    sel = torch.empty(max(plan.totals["sel"], 1), dtype=torch.int32, device=dev)
+    sel_scores = torch.empty(max(plan.totals["sel"], 1), dtype=torch.float32, device=dev)
+    _cabi.head_scores(plan.base_ptr, plan.d_utts, plan.B, plan.n_heads, plan.max_tokens, plan.max_frames,
+                      w_colnorm, w_rownorm, w_coverage, scores)
+    _cabi.topk_heads(scores, plan.d_utts, plan.B, plan.n_heads, sel, sel_scores)
+    return scores, sel, sel_scores
+
+
+def _score_table(sel_host, score_host, n_heads_per_layer):
+    return [
+        (float(s), (int(i) // n_heads_per_layer, int(i) % n_heads_per_layer),
+         f"sample_layer{int(i) // n_heads_per_layer}_head{int(i) % n_heads_per_layer}")
+        for i, s in zip(sel_host, score_host)
+    ]
+
+
+def filter_attention(attns, topk=20, w_colnorm=1, w_rownorm=1, w_coverage=0):
+    """Drop-in for reference timing.py:13-43.  attns: (layers, heads, tokens, frames).
+    Returns ([attns[l,h].unsqueeze(0) ...] ascending by score, [(score, (l,h), name) ...])."""
+    attns = attns if attns.is_contiguous() else attns.contiguous()
+    n_heads = attns.shape[0] * attns.shape[1]
+    # python slicing semantics of `sorted(scores)[-topk:]`
+    if topk > 0:
+        k = min(int(topk), n_heads)
+    elif topk == 0:
+        k = n_heads
+    else:
+        k = max(n_heads + int(topk), 0)
+    plan = _Plan([attns], 0, [k])
+    _, sel, sel_scores = _score_and_select(plan, w_colnorm, w_rownorm, w_coverage)
+    sel_h = sel[:k].cpu().numpy()
+    score_h = sel_scores[:k].cpu().numpy()
+    H = attns.shape[1]
+    table = _score_table(sel_h, score_h, H)
+    return [attns[l, h].unsqueeze(0) for _, (l, h), _ in table], table
+
+
+# ---------------------------------------------------------------------------------
+# force_align
+# ---------------------------------------------------------------------------------
+_SENTINEL = lambda: [[], [], [], [], None]  # noqa: E731  (what the reference returns on EOT-only input)
+
+
+def force_align_batch(ws_list, tokens_list, tokenizer, aligned_unit_type="subword", aggregation="mean", topk=-1,
+                      w_colnorm=1.0, w_rownorm=1.0, w_coverage=0.0):
+    """Batched force_align: one launch per stage for the whole list, one sync at the end.
+    Returns a list with, per utterance, what reference force_align returns."""
+    B = len(ws_list)
+    if B == 0:
+        return []
+    if aggregation not in ("mean", "topk", "grad_norm"):
+        # the reference falls through to `matrix[...]` with `matrix` never bound (timing.py:102)
+        raise UnboundLocalError("cannot access local variable 'matrix' where it is not associated with a value")
+    if aggregation == "topk":
+        assert topk > 0
+    sot_len = len(tokenizer.sot_sequence)
+
+    # host side: word grouping defines the boundaries the device gathers (timing.py:105-108)
+    words_all, wb_all = [], []
+    for toks in tokens_list:
+        words, word_tokens = split_tokens_on_spaces(list(toks) + [tokenizer.eot], tokenizer, aligned_unit_type)
+        words_all.append((words, word_tokens))
+        wb_all.append(np.pad(np.cumsum([len(t) for t in word_tokens[:-1]]), (1, 0)).astype(np.int32))
+    word_counts = [max(len(wt) - 1, 0) for _, wt in words_all]
+
+    if aggregation == "grad_norm":
+        maps = [w.reshape(1, 1, *w.shape[-2:]) for w in ws_list]  # caller-provided (T, F) matrices
+        maps = [m if m.is_contiguous() else m.contiguous() for m in maps]
+    else:
+        maps = [w if w.is_contiguous() else w.contiguous() for w in ws_list]
+    L = [m.shape[0] for m in maps]
+    H = [m.shape[1] for m in maps]
+    if aggregation == "topk":
+        n_sel = [min(int(topk), l * h) for l, h in zip(L, H)]
+    else:
+        n_sel = [(l - l // 2) * h for l, h in zip(L, H)]  # "mean": layers L//2 .. L-1 (timing.py:87-88)
+    plan = _Plan(maps, sot_len, n_sel, word_counts)
+    dev = plan.device
+
+    sel_scores = None
+    if aggregation == "topk":
+        _, sel, sel_scores = _score_and_select(plan, w_colnorm, w_rownorm, w_coverage)
+    else:
+        sel_host = np.concatenate([np.arange((l // 2) * h, l * h, dtype=np.int32) for l, h in zip(L, H)])
+        sel = torch.from_numpy(sel_host).to(dev, non_blocking=True)
+
+    matrix = torch.empty(max(plan.totals["matrix"], 1), dtype=torch.float32, device=dev)
+    if aggregation == "grad_norm":
+        for b, m in enumerate(maps):  # matrix = ws[sot_len:-1] (timing.py:99-102)
+            r = plan.recs[b]
+            n = int(r["row_end"] - r["row_begin"]) * int(r["n_frames"])
+            matrix[int(r["matrix_off"]): int(r["matrix_off"]) + n].copy_(m[0, 0, int(r["row_begin"]): int(r["row_end"])].reshape(-1))
+    else:
+        _cabi.aggregate_heads(plan.base_ptr, sel, plan.d_utts, B, plan.max_tokens, plan.max_frames, matrix)
+
+    wb_flat = np.concatenate([
+        np.pad(wb, (0, wc + 1 - len(wb))) if len(wb) < wc + 1 else wb[: wc + 1] for wb, wc in zip(wb_all, word_counts)
+    ]).astype(np.int32)
+    d_wb = torch.from_numpy(wb_flat).to(dev, non_blocking=True)
+    times = torch.empty(2, plan.totals["word"], dtype=torch.float64, device=dev)
+    trace_bytes = _cabi.dtw_workspace_bytes(B, plan.max_rows, plan.max_frames)
+    trace_ws = torch.empty(trace_bytes, dtype=torch.uint8, device=dev) if trace_bytes else None
+    _cabi.dtw_align(matrix.data_ptr(), plan.d_utts, B, plan.max_rows, plan.max_frames, True, word_bounds=d_wb,
+                    start_times=times[0], end_times=times[1], trace_ws=trace_ws)
+
+    # the only device->host traffic of the call: matrix (returned to the caller, as the
+    # reference does at timing.py:102), W start/end times, k selected heads
+    matrix_h = matrix.cpu()
+    times_h = times.cpu().numpy()
+    if sel_scores is not None:
+        sel_h = sel.cpu().numpy()
+        sel_scores_h = sel_scores.cpu().numpy()
+
+    results = []
+    for b in range(B):
+        r = plan.recs[b]
+        words, word_tokens = words_all[b]
+        if len(word_tokens) <= 1:
+            results.append(_SENTINEL())
+            continue
+        n_rows, F = int(r["row_end"] - r["row_begin"]), int(r["n_frames"])
+        mo, wo, W = int(r["matrix_off"]), int(r["word_off"]), word_counts[b]
+        scores = None
+        if sel_scores is not None:
+            so, k = int(r["sel_off"]), int(r["n_sel"])
+            scores = _score_table(sel_h[so: so + k], sel_scores_h[so: so + k], H[b])
+        results.append((words, times_h[0, wo: wo + W].copy(), times_h[1, wo: wo + W].copy(),
+                        matrix_h[mo: mo + n_rows * F].view(n_rows, F), scores))
+    return results
+
+
+def force_align(ws, tokens, tokenizer, aligned_unit_type="subword", aggregation="mean", topk=-1,
+                w_colnorm=1.0, w_rownorm=1.0, w_coverage=0.0):
+    """Drop-in for reference timing.py:69-114.
+    ws: (layers, heads, tokens, frames) attention weights ((T, F) for aggregation='grad_norm');
+    tokens: python list of the text tokens only.
+    Returns (words, start_times, end_times, matrix, scores) or the list [[], [], [], [], None]
+    when only EOT remains."""
+    return force_align_batch([ws], [tokens], tokenizer, aligned_unit_type, aggregation, topk, w_colnorm, w_rownorm,
+                             w_coverage)[0]
+
+
+# ---------------------------------------------------------------------------------
+# dtw (whisper.timing.dtw as the reference calls it at timing.py:103)
+# ---------------------------------------------------------------------------------
+def dtw_batch(costs: Sequence[torch.Tensor]):
+    """costs: list of (N_b, M_b) fp32 CUDA tensors.  Returns [(text_indices, time_indices)] int64 numpy,
+    bit-identical to upstream dtw_cpu on the same matrix."""
+    B = len(costs)
+    xs = [c.detach().float().contiguous() for c in costs]
+    dev = xs[0].device
+    if dev.type != "cuda":
+        raise _cabi.WcaError("dtw: CUDA tensor required (no CPU fallback exists)")
+    base = xs[0].data_ptr()
+    recs = np.zeros(B, dtype=_cabi.UTT_DTYPE)
+    path_off = 0
+    for b, x in enumerate(xs):
+        n, m = int(x.shape[0]), int(x.shape[1])
+        r = recs[b]
+        r["n_tokens"], r["n_frames"], r["row_begin"], r["row_end"] = n, m, 0, n
+        r["matrix_off"] = (x.data_ptr() - base) // 4
+        r["path_off"] = path_off
+        r["jump_off"] = 0
+        path_off += n + m
+    d_utts = _cabi.upload_utts(recs, dev)
+    max_rows = int(recs["row_end"].max())
+    max_frames = int(recs["n_frames"].max())
+    p_text = torch.empty(max(path_off, 1), dtype=torch.int32, device=dev)
+    p_time = torch.empty(max(path_off, 1), dtype=torch.int32, device=dev)
+    p_len = torch.zeros(B, dtype=torch.int32, device=dev)
+    trace_bytes = _cabi.dtw_workspace_bytes(B, max_rows, max_frames)
+    trace_ws = torch.empty(trace_bytes, dtype=torch.uint8, device=dev) if trace_bytes else None
+    _cabi.dtw_align(base, d_utts, B, max_rows, max_frames, False, path_text=p_text, path_time=p_time, path_len=p_len,
+                    trace_ws=trace_ws)
+    pt, pj, pl = p_text.cpu().numpy(), p_time.cpu().numpy(), p_len.cpu().numpy()
+    out = []
+    for b in range(B):
+        end = int(recs[b]["path_off"]) + int(recs[b]["row_end"]) + int(recs[b]["n_frames"])
+        out.append((pt[end - pl[b]: end].astype(np.int64), pj[end - pl[b]: end].astype(np.int64)))
+    return out
+
+
+def dtw(x: torch.Tensor):
+    """(text_indices, time_indices) of the min-cost monotone path through cost matrix x (N, M)."""
+    return dtw_batch([x])[0]

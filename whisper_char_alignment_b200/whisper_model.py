@@ -1,0 +1,222 @@
+"""Whisper encoder/decoder on PyTorch + cuBLAS -- the part of the path that north_star
+leaves on library GEMMs.
+
+`openai-whisper` is not installable offline, so the product carries its own module with
+the published architecture and the published parameter names: a checkpoint's
+`model_state_dict` (or the oracle's seeded random init) loads with `load_state_dict`.
+Differences from the upstream module that matter for this path:
+
+  * attention always runs through `scaled_dot_product_attention`; the encoder never
+    materialises its 1500x1500 maps (the reference's `disable_sdpa()` wraps the whole
+    forward, timing.py:57-58, and pays for 24 x 144 MB of encoder maps nobody reads);
+  * cross-attention logits are NOT produced here.  `timing.get_attentions` taps the
+    outputs of `cross_attn.query` / `cross_attn.key` and hands them to the sm_100a
+    capture kernel, so any module with this tree (including a stock upstream model)
+    works as `model`;
+  * the decoder accepts right-padded token batches (causal masking makes the padding
+    invisible to the real positions).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import asdict, dataclass
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+@dataclass
+class ModelDimensions:
+    n_mels: int
+    n_audio_ctx: int
+    n_audio_state: int
+    n_audio_head: int
+    n_audio_layer: int
+    n_vocab: int
+    n_text_ctx: int
+    n_text_state: int
+    n_text_head: int
+    n_text_layer: int
+
+
+#: published sizes: (mels, audio ctx, width, heads, layers, vocab, text ctx, width, heads, layers)
+SIZES = {
+    "tiny": (80, 1500, 384, 6, 4, 51865, 448, 384, 6, 4),
+    "base": (80, 1500, 512, 8, 6, 51865, 448, 512, 8, 6),
+    "small": (80, 1500, 768, 12, 12, 51865, 448, 768, 12, 12),
+    "medium": (80, 1500, 1024, 16, 24, 51865, 448, 1024, 16, 24),
+    "large-v3": (128, 1500, 1280, 20, 32, 51866, 448, 1280, 20, 32),
+}
+
+
+def dims_for(name: str) -> ModelDimensions:
+    return ModelDimensions(*SIZES[name])
+
+
+class _Norm(nn.LayerNorm):
+    def forward(self, x):
+        return super().forward(x.float()).to(x.dtype)
+
+
+class _Proj(nn.Linear):
+    def forward(self, x):
+        bias = self.bias if self.bias is None else self.bias.to(x.dtype)
+        return F.linear(x, self.weight.to(x.dtype), bias)
+
+
+class _Conv(nn.Conv1d):
+    def _conv_forward(self, x, weight, bias):
+        return super()._conv_forward(x, weight.to(x.dtype), None if bias is None else bias.to(x.dtype))
+
+
+class Attention(nn.Module):
+    """query/key/value/out projections (key without bias) around SDPA."""
+
+    def __init__(self, width: int, heads: int):
+        super().__init__()
+        self.n_head = heads
+        self.query = _Proj(width, width)
+        self.key = _Proj(width, width, bias=False)
+        self.value = _Proj(width, width)
+        self.out = _Proj(width, width)
+
+    def _split(self, t):
+        b, n, _ = t.shape
+        return t.view(b, n, self.n_head, -1).transpose(1, 2)
+
+    def forward(self, x, xa=None, causal: bool = False):
+        src = x if xa is None else xa
+        q, k, v = self._split(self.query(x)), self._split(self.key(src)), self._split(self.value(src))
+        # SDPA's default scale is d_head^-1/2 == (d_head^-1/4)^2, the published scaling
+        ctx = F.scaled_dot_product_attention(q, k, v, is_causal=causal and q.shape[2] > 1)
+        return self.out(ctx.transpose(1, 2).flatten(2)), None
+
+
+class Block(nn.Module):
+    def __init__(self, width: int, heads: int, cross: bool):
+        super().__init__()
+        self.attn = Attention(width, heads)
+        self.attn_ln = _Norm(width)
+        self.cross_attn = Attention(width, heads) if cross else None
+        self.cross_attn_ln = _Norm(width) if cross else None
+        self.mlp = nn.Sequential(_Proj(width, 4 * width), nn.GELU(), _Proj(4 * width, width))
+        self.mlp_ln = _Norm(width)
+
+    def forward(self, x, xa=None, causal: bool = False):
+        x = x + self.attn(self.attn_ln(x), causal=causal)[0]
+        if self.cross_attn is not None:
+            x = x + self.cross_attn(self.cross_attn_ln(x), xa)[0]
+        return x + self.mlp(self.mlp_ln(x))
+
+
+def _sinusoid_table(length: int, width: int, max_timescale: float = 10000.0):
+    half = width // 2
+    rates = torch.exp(-(math.log(max_timescale) / (half - 1)) * torch.arange(half))
+    phase = torch.arange(length)[:, None] * rates[None, :]
+    return torch.cat([phase.sin(), phase.cos()], dim=1)
+
+
+class AudioEncoder(nn.Module):
+    def __init__(self, n_mels, n_ctx, width, heads, layers):
+        super().__init__()
+        self.conv1 = _Conv(n_mels, width, kernel_size=3, padding=1)
+        self.conv2 = _Conv(width, width, kernel_size=3, stride=2, padding=1)
+        self.register_buffer("positional_embedding", _sinusoid_table(n_ctx, width))
+        self.blocks = nn.ModuleList([Block(width, heads, cross=False) for _ in range(layers)])
+        self.ln_post = _Norm(width)
+
+    def forward(self, mel):
+        x = F.gelu(self.conv2(F.gelu(self.conv1(mel)))).transpose(1, 2)
+        if x.shape[1:] != self.positional_embedding.shape:
+            raise ValueError(f"incorrect audio shape {tuple(mel.shape)}: expected {2 * self.positional_embedding.shape[0]} frames")
+        x = (x + self.positional_embedding).to(x.dtype)
+        for blk in self.blocks:
+            x = blk(x)
+        return self.ln_post(x)
+
+
+class TextDecoder(nn.Module):
+    def __init__(self, n_vocab, n_ctx, width, heads, layers):
+        super().__init__()
+        self.token_embedding = nn.Embedding(n_vocab, width)
+        self.positional_embedding = nn.Parameter(torch.empty(n_ctx, width))
+        self.blocks = nn.ModuleList([Block(width, heads, cross=True) for _ in range(layers)])
+        self.ln = _Norm(width)
+
+    def forward(self, tokens, xa):
+        x = self.token_embedding(tokens) + self.positional_embedding[: tokens.shape[-1]]
+        x = x.to(xa.dtype)
+        for blk in self.blocks:
+            x = blk(x, xa, causal=True)
+        x = self.ln(x)
+        return (x @ self.token_embedding.weight.to(x.dtype).t()).float()
+
+
+class Whisper(nn.Module):
+    def __init__(self, dims: ModelDimensions):
+        super().__init__()
+        self.dims = dims
+        self.encoder = AudioEncoder(dims.n_mels, dims.n_audio_ctx, dims.n_audio_state, dims.n_audio_head,
+                                    dims.n_audio_layer)
+        self.decoder = TextDecoder(dims.n_vocab, dims.n_text_ctx, dims.n_text_state, dims.n_text_head,
+                                   dims.n_text_layer)
+        upper = torch.zeros(dims.n_text_layer, dims.n_text_head, dtype=torch.bool)
+        upper[dims.n_text_layer // 2:] = True
+        self.register_buffer("alignment_heads", upper.to_sparse(), persistent=False)
+
+    def embed_audio(self, mel):
+        return self.encoder(mel)
+
+    def logits(self, tokens, audio_features):
+        return self.decoder(tokens, audio_features)
+
+    def forward(self, mel, tokens):
+        return self.decoder(tokens, self.encoder(mel))
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @property
+    def is_multilingual(self):
+        return self.dims.n_vocab >= 51865
+
+    @property
+    def num_languages(self):
+        return self.dims.n_vocab - 51765 - int(self.is_multilingual)
+
+
+def load_model(name_or_path: str, device=None, *, seed: int = 0, qk_gain: float = 1.0) -> Whisper:
+    """A checkpoint file ({"dims", "model_state_dict"}) if `name_or_path` is a path, else a
+    seeded random-init model of the named size (no checkpoints are reachable offline)."""
+    import os
+
+    if os.path.isfile(name_or_path):
+        ckpt = torch.load(name_or_path, map_location="cpu", weights_only=True)
+        model = Whisper(ModelDimensions(**ckpt["dims"]))
+        model.load_state_dict(ckpt["model_state_dict"])
+    else:
+        model = random_init(dims_for(name_or_path), seed=seed, qk_gain=qk_gain)
+    model.eval()
+    return model if device is None else model.to(device)
+
+
+def random_init(dims: ModelDimensions, seed: int = 0, qk_gain: float = 1.0) -> Whisper:
+    """Seeded synthetic weights.  `qk_gain` scales the cross-attention query/key projections
+    so that the maps are peaky enough for alignment paths to be data-driven."""
+    keep = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    model = Whisper(dims)
+    with torch.no_grad():
+        model.decoder.positional_embedding.normal_(0, 0.02)
+        for blk in model.decoder.blocks:
+            blk.cross_attn.query.weight.mul_(qk_gain)
+            blk.cross_attn.query.bias.mul_(qk_gain)
+            blk.cross_attn.key.weight.mul_(qk_gain)
+    torch.random.set_rng_state(keep)
+    return model.eval()
+
+
+def save_checkpoint(model: Whisper, path: str):
+    torch.save({"dims": asdict(model.dims), "model_state_dict": model.state_dict()}, path)
