@@ -8,11 +8,6 @@
 
 namespace wca {
 
-struct LayerPtrs {
-    const float *q[WCA_MAX_LAYERS];
-    const float *k[WCA_MAX_LAYERS];
-};
-
 constexpr int kTokTile = 32;    // tokens per CTA
 constexpr int kFrmTile = 64;    // frames per inner chunk
 constexpr int kKStride = kHeadDim + 1;  // +1 float: lane<->frame reads hit distinct banks

@@ -35,6 +35,12 @@ void count_launch();
         ::wca::count_launch();                             \
     } while (0)
 
+// Per-layer Q / K base pointers, passed to the capture kernels by value.
+struct LayerPtrs {
+    const float *q[WCA_MAX_LAYERS];
+    const float *k[WCA_MAX_LAYERS];
+};
+
 constexpr int kHeadDim = 64;   // every published Whisper size has d_head = 64
 constexpr int kWarp = 32;
 
