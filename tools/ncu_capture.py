@@ -1,0 +1,45 @@
+"""One capture launch at a BASELINE.json shape, for ncu.  usage: ncu_capture.py [timit|libri] [B] [simt]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from whisper_char_alignment_b200 import _cabi
+
+shape = sys.argv[1] if len(sys.argv) > 1 else "timit"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+simt = len(sys.argv) > 3 and sys.argv[3] == "simt"
+reps = 3
+dev = torch.device("cuda:0")
+L, H, D, n_ctx = 24, 16, 64, 1500
+rng = np.random.default_rng(0)
+if shape == "timit":
+    Ts = rng.integers(35, 56, B); Fs = rng.integers(100, 200, B)
+else:
+    Fs = rng.integers(100, 1500, B); Ts = np.minimum(448, (Fs * 0.27).astype(int) + 5)
+t_max = int(Ts.max())
+q = [torch.randn(B, t_max, H * D, device=dev) for _ in range(L)]
+k = [torch.randn(B, n_ctx, H * D, device=dev) for _ in range(L)]
+recs = np.zeros(B, dtype=_cabi.UTT_DTYPE)
+off = 0
+for b in range(B):
+    recs[b]["n_tokens"], recs[b]["n_frames"] = Ts[b], Fs[b]
+    recs[b]["q_row0"], recs[b]["k_row0"], recs[b]["ws_off"] = b * t_max, b * n_ctx, off
+    off += L * H * int(Ts[b]) * int(Fs[b])
+d_utts = _cabi.upload_utts(recs, dev)
+ws = torch.empty(off, device=dev)
+flags = _cabi.WCA_CAPTURE_FORCE_SIMT if simt else 0
+bytes_alg = 4 * off + sum(4 * L * (int(t) + int(f)) * H * D for t, f in zip(Ts, Fs))
+for _ in range(2):
+    _cabi.capture_attention(q, k, H, H * D, H * D, d_utts, B, t_max, int(Fs.max()), 3, 1.0, ws, flags)
+torch.cuda.synchronize()
+a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+tot = 0.0
+for _ in range(reps):
+    flush.zero_()
+    a.record()
+    _cabi.capture_attention(q, k, H, H * D, H * D, d_utts, B, t_max, int(Fs.max()), 3, 1.0, ws, flags)
+    b_.record(); torch.cuda.synchronize()
+    tot += a.elapsed_time(b_)
+ms = tot / reps
+print(f"{shape} B={B} {'simt+filter' if simt else 'tcgen05'}: {ms:.3f} ms/launch, algorithmic {bytes_alg/1e6:.1f} MB -> {bytes_alg/ms/1e6:.1f} GB/s "
+      f"({bytes_alg/ms/1e6/6548.5*100:.1f}% of measured HBM peak)")

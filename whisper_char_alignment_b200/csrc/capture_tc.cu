@@ -218,8 +218,9 @@ __device__ __forceinline__ void split_stage(const unsigned char *stage, unsigned
         float h[4], l[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            h[c] = __uint_as_float(__float_as_uint(x[c]) & 0xFFFFE000u);   // tf32 keeps 10 mantissa bits
-            l[c] = __uint_as_float(__float_as_uint(x[c] - h[c]) & 0xFFFFE000u);  // x - h is exact in fp32
+            // round-to-nearest onto the 10-bit tf32 mantissa; x - h is exact in fp32 (may be negative)
+            h[c] = __uint_as_float((__float_as_uint(x[c]) + 0x1000u) & 0xFFFFE000u);
+            l[c] = __uint_as_float((__float_as_uint(x[c] - h[c]) + 0x1000u) & 0xFFFFE000u);
         }
         const uint32_t off = (uint32_t)ch * lbo + (uint32_t)(row + row_off) * 16u;
         *reinterpret_cast<float4 *>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
