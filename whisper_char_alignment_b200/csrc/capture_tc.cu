@@ -1,65 +1,73 @@
-// tcgen05 / TMEM / TMA cross-attention capture (north-star kernel 1).
+// tcgen05 / TMEM / TMA cross-attention capture (north-star kernel 1), v2: persistent,
+// warp-specialised, double-buffered in tensor memory.
 //
-// Replaces reference timing.py:50-66 + upstream qkv_attention (SDPA off): for one
-// (utterance, layer, head, block of 128 tokens) a CTA -- or a cluster of CTAs when the
-// utterance has more frames than one CTA's tensor memory holds -- computes
+// Replaces reference timing.py:50-66 + upstream qkv_attention (SDPA off): for every
+// (utterance, layer, head, block of 128 tokens) it computes
 //     P[t, f] = softmax_f( median_w( (q_t * s) . (k_f * s) )[:F] * qk_scale ),  s = 64^-1/4
 // and writes it ONCE, already trimmed to F, in the (L, H, T, F) layout get_attentions
 // returns.  The 1500-frame logits, the torch.cat copy, the reflect-padded copy and the two
 // softmax passes of the reference never touch HBM.
 //
 // Mapping
-//   tokens  <-> TMEM lanes (UMMA M = 128): thread r of an epilogue warp owns token row r, so
-//               the median window and both softmax reductions are private to a thread;
+//   tokens  <-> TMEM lanes (UMMA M = 128): thread r of an epilogue warpgroup owns token row
+//               r, so the median window and both softmax reductions are private to a thread;
 //   frames  <-> TMEM columns: the fp32 accumulator IS the row buffer (filter and exp results
-//               are written back in place with tcgen05.st), 464 own frames + 2 x 16 halo
-//               columns per CTA;
-//   F > 464 : thread-block cluster of 2/4/8 CTAs along frames; per-row max and sum are
-//               exchanged through distributed shared memory (2 cluster barriers per tile);
-//   fp32 in, fp32-grade out on the tensor pipe: every operand is split v = hi + lo with
-//               hi = tf32-truncated v, and hi*hi + hi*lo + lo*hi is accumulated (3 x 8
-//               tcgen05.mma kind::tf32 per 64-frame chunk; |error| ~ 2^-21 relative);
-//   TMA     : Q / K rows arrive by cp.async.bulk (256 B per head row) on an mbarrier into a
-//               padded staging tile; converter threads split them into the no-swizzle
-//               K-major UMMA layout [k-chunk][8-row group][8 rows][16 B].
+//               are written back in place with tcgen05.st).  512 columns = two accumulators
+//               of 256 (16 halo + 224 own + 16 halo), so the tensor pipe fills one while an
+//               epilogue warpgroup drains the other;
+//   F > 224 : thread-block cluster of 2/4/8 CTAs along frames; per-row max and sum travel
+//               through distributed shared memory, signalled with remote mbarrier arrives;
+//   fp32 in, fp32-grade out on the tensor pipe: operands are split v = hi + lo (hi, lo
+//               rounded to tf32) and lo*hi + hi*lo + hi*hi is accumulated: 3 x 8
+//               tcgen05.mma kind::tf32 per 64-frame chunk, error ~1e-6 relative;
+//   TMA     : Q / K head rows (256 B) arrive by cp.async.bulk on mbarriers into a 3-stage
+//               staging ring; splitter warps rewrite them into the no-swizzle K-major UMMA
+//               layout [k-chunk][8-row group][8 rows][16 B].
 //
-// v1 schedule: load/convert/MMA are pipelined against each other per 64-frame chunk; the
-// three epilogue sweeps start when the last MMA has committed.
+// Roles of the 16 warps of a CTA (one persistent CTA per SM, static tile schedule):
+//   warp 0      TMA producer            warp 1      MMA issuer (one thread)
+//   warps 4-7   operand splitters       warps 8-11 / 12-15   epilogue warpgroups A / B,
+//                                       alternating tiles (accumulator i & 1)
 #include "common.cuh"
 
 namespace wca {
-
 namespace tc {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr int kRows = 128;           // UMMA M: tokens per tile
 constexpr int kChunk = 64;           // frames per MMA group (UMMA N of a full chunk)
-constexpr int kHalo = 16;            // halo columns on either side (>= WCA max half-width 15)
-constexpr int kOwnCol0 = 16;         // TMEM column of a CTA's first own frame
-constexpr int kMaxOwn = 464;         // own frames per CTA: 16 + 464 + 16 <= 496 columns
+constexpr int kHalo = 16;            // halo columns either side (>= largest half-width, 15)
+constexpr int kOwnCol0 = 16;         // accumulator column of a CTA's first own frame
+constexpr int kAccCols = 256;        // columns per accumulator
+constexpr int kMaxOwn = kAccCols - 2 * kHalo;   // 224 own frames per CTA and tile
 constexpr int kTmemCols = 512;
 constexpr int kRowBytes = kHeadDim * 4;          // 256
 constexpr int kStagePitch = kRowBytes + 16;      // padded: conflict-free 16-byte column reads
 constexpr int kStageRows = 64;
 constexpr int kStageBytes = kStageRows * kStagePitch;   // 17408
+constexpr int kStages = 3;
 constexpr int kQSplitBytes = kRows * kRowBytes;         // 32768 per hi / lo
 constexpr int kKSplitBytes = kChunk * kRowBytes;        // 16384 per hi / lo per buffer
 constexpr uint32_t kLboQ = kRows * 16;   // bytes between consecutive 16-byte k-chunks (A operand)
 constexpr uint32_t kLboK = kChunk * 16;  // same for the B operand
 constexpr uint32_t kSbo = 128;           // bytes between consecutive 8-row groups
+constexpr int kTilePitch = 17;           // transpose tile pitch (odd: conflict-free column writes)
+constexpr int kSplitThreads = 128;
+constexpr int kEpiThreads = 128;
 
 constexpr int kOffStage = 0;
-constexpr int kOffQHi = kOffStage + 2 * kStageBytes;
+constexpr int kOffQHi = kOffStage + kStages * kStageBytes;
 constexpr int kOffQLo = kOffQHi + kQSplitBytes;
 constexpr int kOffKHi = kOffQLo + kQSplitBytes;
 constexpr int kOffKLo = kOffKHi + 2 * kKSplitBytes;
-constexpr int kOffStat = kOffKLo + 2 * kKSplitBytes;      // smax[128], ssum[128]
-constexpr int kOffBar = kOffStat + 2 * kRows * 4;          // full[2], kfree[2], done
-constexpr int kOffTmem = kOffBar + 5 * 8;
+constexpr int kOffTile = kOffKLo + 2 * kKSplitBytes;            // 8 epilogue warps x 32 x 17 floats
+constexpr int kOffStat = kOffTile + 8 * 32 * kTilePitch * 4;    // smax[2][128], ssum[2][128]
+constexpr int kOffBar = kOffStat + 4 * kRows * 4;
+enum Bar { kStageFull = 0, kStageEmpty = 3, kAReady = 6, kAFree = 7, kBReady = 8, kBFree = 10, kAccFull = 12,
+           kAccEmpty = 14, kXMax = 16, kXSum = 18, kNumBars = 20 };
+constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-constexpr int kTilePitch = 17;  // odd pitch: conflict-free column writes
-static_assert(4 * 32 * kTilePitch * 4 <= 2 * kStageBytes, "epilogue transpose tiles reuse the staging area");
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -78,16 +86,26 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ float ld_dsmem_f32(const float *local, uint32_t rank) {
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem, uint32_t rank) {
     uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem), "r"(rank));
+    return remote;
+}
+__device__ __forceinline__ float ld_dsmem_f32(const float *local, uint32_t rank) {
     float v;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local)), "r"(rank));
-    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(map_to_rank(smem_u32(local), rank)) : "memory");
     return v;
 }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t rank) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(map_to_rank(local_bar, rank))
+                 : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -105,9 +123,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded waits: a protocol bug must surface as a launch failure, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait_cluster(bar, parity); ++spins)
         if (spins > (1u << 24)) __trap();
 }
 // TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
@@ -118,6 +153,9 @@ __device__ __forceinline__ void tma_load_row(uint32_t dst, const void *src, uint
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
@@ -130,7 +168,6 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, both operands K-major, tf32 inputs, fp32 accumulate.
@@ -163,55 +200,115 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
+// Asynchronous TMEM load of 16 consecutive columns of this thread's lane; the registers
+// are only valid after tmem_ld_wait(), which names them so no use can be hoisted above it.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
         : "r"(taddr)
         : "memory");
-    tmem_wait_ld();
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait(float (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                   "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+                 :
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
             taddr),
-        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
-        "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
-        "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+        "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
         : "memory");
 }
 __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
-    uint32_t r;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-    tmem_wait_ld();
-    return __uint_as_float(r);
+    float r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=f"(r)
+                 : "r"(taddr)
+                 : "memory");
+    return r;
 }
 __device__ __forceinline__ void tmem_st1(uint32_t taddr, float v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(__float_as_uint(v)) : "memory");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
-// ------------------------------------------------------------------ building blocks
-// One warp streams `n_valid` 256-byte head rows into a staging tile; bar expects the bytes.
-__device__ __forceinline__ void producer_load(uint32_t stage, const float *src, int64_t ld, int n_valid, uint32_t bar,
-                                              int lane) {
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)n_valid * kRowBytes);
+// ------------------------------------------------------------------ tile geometry
+struct KernelArgs {
+    const wca_utt_t *utts;
+    float *ws;
+    int64_t ld_q, ld_k;
+    int n_heads, lh_count, tok_blocks, n_tiles;
+    float s, qk_scale;
+    int raw_logits;
+};
+
+struct Geo {
+    bool live;       // the tile has token rows (same answer in every CTA of the cluster)
+    int T, F, rows_valid;
+    int f0, f1, n_own;       // frames this CTA owns
+    int half;                // filter half-width actually applied (0: identity)
+    int m0, mcol0, n_mma;    // first frame / accumulator column / frame count the MMA computes
+    int n_chunks;
+    const float *qsrc, *ksrc;
+    float *out;              // row 0 of this tile, frame 0
+};
+
+template <int W>
+__device__ __forceinline__ Geo decode_tile(const LayerPtrs &ptrs, const KernelArgs &a, int tile, uint32_t crank,
+                                           uint32_t csize) {
+    Geo g;
+    const int tb = tile % a.tok_blocks;
+    const int lh = (tile / a.tok_blocks) % a.lh_count;
+    const int ub = tile / (a.tok_blocks * a.lh_count);
+    const wca_utt_t u = a.utts[ub];
+    g.T = u.n_tokens;
+    g.F = u.n_frames;
+    const int t0 = tb * kRows;
+    g.live = t0 < g.T;
+    g.rows_valid = min(kRows, g.T - t0);
+    const int layer = lh / a.n_heads, head = lh % a.n_heads;
+    g.qsrc = ptrs.q[layer] + (u.q_row0 + t0) * a.ld_q + (int64_t)head * kHeadDim;
+    g.ksrc = ptrs.k[layer] + u.k_row0 * a.ld_k + (int64_t)head * kHeadDim;
+    g.out = a.ws + u.ws_off + ((int64_t)lh * g.T + t0) * g.F;
+    const int slab = (((g.F + (int)csize - 1) / (int)csize) + 15) & ~15;
+    g.f0 = (int)crank * slab;
+    g.f1 = min(g.F, g.f0 + slab);
+    g.n_own = max(0, g.f1 - g.f0);
+    const bool filter = !a.raw_logits && W > 1 && g.F > W / 2;  // identity for very short rows, like upstream
+    g.half = filter ? W / 2 : 0;
+    g.m0 = g.f0 > 0 ? g.f0 - kHalo : 0;
+    g.mcol0 = g.f0 > 0 ? 0 : kOwnCol0;  // frame f always sits at accumulator column f - f0 + 16
+    g.n_mma = g.n_own > 0 ? min(g.f1 + kHalo, g.F) - g.m0 : 0;
+    g.n_chunks = (g.n_mma + kChunk - 1) / kChunk;
+    return g;
+}
+
+// ------------------------------------------------------------------ role bodies
+__device__ __forceinline__ void producer_item(uint32_t stage, uint32_t bar_full, uint32_t bar_empty, uint32_t n_item,
+                                              const float *src, int64_t ld, int n_valid, int lane) {
+    mbar_wait(bar_empty, ((n_item / kStages) & 1u) ^ 1u);  // first lap passes immediately
+    if (lane == 0) mbar_expect_tx(bar_full, (uint32_t)n_valid * kRowBytes);
     __syncwarp();
     for (int r = lane; r < n_valid; r += kWarp)
-        tma_load_row(stage + r * kStagePitch, src + (int64_t)r * ld, kRowBytes, bar);
+        tma_load_row(stage + r * kStagePitch, src + (int64_t)r * ld, kRowBytes, bar_full);
 }
 
-// All threads: staging tile (64 rows) -> scaled hi / lo halves in UMMA no-swizzle layout.
+// 128 splitter threads: staging tile (64 rows) -> scaled hi / lo parts in UMMA no-swizzle layout.
 __device__ __forceinline__ void split_stage(const unsigned char *stage, unsigned char *hi, unsigned char *lo,
-                                            uint32_t lbo, int row_off, float s, int tid) {
+                                            uint32_t lbo, int row_off, float s, int t) {
 #pragma unroll
-    for (int it = 0; it < (kStageRows * 16) / kThreads; ++it) {
-        const int e = it * kThreads + tid;
+    for (int it = 0; it < (kStageRows * 16) / kSplitThreads; ++it) {
+        const int e = it * kSplitThreads + t;
         const int row = e & (kStageRows - 1), ch = e >> 6;
         const float4 v = *reinterpret_cast<const float4 *>(stage + row * kStagePitch + ch * 16);
         const float x[4] = {v.x * s, v.y * s, v.z * s, v.w * s};
@@ -229,19 +326,12 @@ __device__ __forceinline__ void split_stage(const unsigned char *stage, unsigned
     fence_proxy_async_smem();  // generic-proxy stores must be visible to the tensor core's async proxy
 }
 
-// Sliding median over a 16-column block with its neighbour blocks; all indices are compile
-// time after unrolling, so everything stays in registers.
+// Sliding median over a 16-column block with its neighbour blocks; every index is a compile
+// time constant after unrolling, so the window lives in registers.
 template <int W>
 __device__ __forceinline__ void median_block(const float (&prev)[16], const float (&cur)[16], const float (&next)[16],
                                              float (&out)[16]) {
     constexpr int half = W / 2;
-    float line[48];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        line[i] = prev[i];
-        line[16 + i] = cur[i];
-        line[32 + i] = next[i];
-    }
 #pragma unroll
     for (int pos = 0; pos < 16; ++pos) {
         if constexpr (W == 1) {
@@ -249,8 +339,139 @@ __device__ __forceinline__ void median_block(const float (&prev)[16], const floa
         } else {
             float win[W];
 #pragma unroll
-            for (int j = 0; j < W; ++j) win[j] = line[16 + pos - half + j];
+            for (int j = 0; j < W; ++j) {
+                const int idx = 16 + pos - half + j;  // position in prev | cur | next
+                win[j] = idx < 16 ? prev[idx] : (idx < 32 ? cur[idx - 16] : next[idx - 32]);
+            }
             out[pos] = median_regs<W>(win);
+        }
+    }
+}
+
+// The three sweeps of one tile by one epilogue warpgroup (thread <-> token row).
+template <int W>
+__device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a, unsigned char *smem, uint32_t acc,
+                                              int grp, int ewarp, int lane, uint32_t csize, uint32_t x_parity) {
+    const int row = ewarp * 32 + lane;
+    const bool row_ok = row < g.rows_valid;
+    const bool sweep = (ewarp * 32 < g.rows_valid) && g.n_own > 0;  // warp-uniform
+    const uint32_t trow = acc + ((uint32_t)(ewarp * 32) << 16) + kOwnCol0;  // own frame 0 of this lane quarter
+    const int n_blocks = (g.n_own + 15) >> 4;
+    float *smax = reinterpret_cast<float *>(smem + kOffStat) + grp * kRows;
+    float *ssum = reinterpret_cast<float *>(smem + kOffStat) + (2 + grp) * kRows;
+    const uint32_t bar_xmax = smem_u32(smem + kOffBar) + 8u * (kXMax + grp);
+    const uint32_t bar_xsum = smem_u32(smem + kOffBar) + 8u * (kXSum + grp);
+
+    float inv_sum = 1.f;
+    if (!a.raw_logits) {
+        float row_max = -INFINITY;
+        if (sweep) {
+            if (g.half > 0) {
+                // materialise the reflect padding in TMEM: frame -i <- frame i, frame F-1+i <- frame F-1-i
+                if (g.f0 == 0)
+                    for (int i = 1; i <= g.half; ++i) tmem_st1(trow - (uint32_t)i, tmem_ld1(trow + (uint32_t)i));
+                for (int f = max(g.F, g.f1); f < g.f1 + g.half; ++f)
+                    tmem_st1(trow + (uint32_t)(f - g.f0), tmem_ld1(trow + (uint32_t)(2 * (g.F - 1) - f - g.f0)));
+                tmem_wait_st();
+            }
+            // sweep A: median filter in place, * qk_scale, running max; the load of block b+2 is in flight
+            float prev[16], cur[16], next[16], ahead[16], med[16];
+            tmem_ld16_issue(trow - 16u, prev);
+            tmem_ld16_issue(trow, cur);
+            tmem_ld16_issue(trow + 16u, next);
+            tmem_ld_wait(prev);
+            tmem_ld_wait(cur);
+            tmem_ld_wait(next);
+            for (int b = 0; b < n_blocks; ++b) {
+                if (b + 2 <= n_blocks) tmem_ld16_issue(trow + (uint32_t)(16 * (b + 2)), ahead);  // stays inside the accumulator
+                if (g.half > 0) {
+                    median_block<W>(prev, cur, next, med);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) med[i] = cur[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    med[i] *= a.qk_scale;
+                    if (16 * b + i < g.n_own) row_max = fmaxf(row_max, med[i]);
+                }
+                tmem_st16(trow + (uint32_t)(16 * b), med);
+                tmem_ld_wait(ahead);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    prev[i] = cur[i];
+                    cur[i] = next[i];
+                    next[i] = ahead[i];
+                }
+            }
+            tmem_wait_st();
+        }
+        // exchange the row maxima across the cluster (every CTA takes part, even with no own frames)
+        smax[row] = row_ok ? row_max : -INFINITY;
+        named_bar_sync(1 + grp, kEpiThreads);
+        if (row == 0)
+            for (uint32_t r = 0; r < csize; ++r) mbar_arrive_remote(bar_xmax, r);
+        mbar_wait_cluster(bar_xmax, x_parity);
+        float gmax = -INFINITY;
+        for (uint32_t r = 0; r < csize; ++r) gmax = fmaxf(gmax, ld_dsmem_f32(&smax[row], r));
+
+        float row_sum = 0.f;
+        if (sweep) {
+            // sweep B: e = exp(x - max) in place, running sum; one block of loads in flight
+            const float kLog2e = 1.4426950408889634f;
+            const float shift = gmax * kLog2e;
+            float v[16], ahead[16];
+            tmem_ld16_issue(trow, v);
+            tmem_ld_wait(v);
+            for (int b = 0; b < n_blocks; ++b) {
+                tmem_ld16_issue(trow + (uint32_t)(16 * (b + 1)), ahead);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    v[i] = ex2_approx(fmaf(v[i], kLog2e, -shift));
+                    if (16 * b + i < g.n_own) row_sum += v[i];
+                }
+                tmem_st16(trow + (uint32_t)(16 * b), v);
+                tmem_ld_wait(ahead);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = ahead[i];
+            }
+            tmem_wait_st();
+        }
+        ssum[row] = row_ok ? row_sum : 0.f;
+        named_bar_sync(1 + grp, kEpiThreads);
+        if (row == 0)
+            for (uint32_t r = 0; r < csize; ++r) mbar_arrive_remote(bar_xsum, r);
+        mbar_wait_cluster(bar_xsum, x_parity);
+        float gsum = 0.f;
+        for (uint32_t r = 0; r < csize; ++r) gsum += ld_dsmem_f32(&ssum[row], r);
+        inv_sum = 1.f / gsum;
+    }
+
+    // sweep C: normalise, transpose 32x16 blocks through shared memory, coalesced row stores
+    if (sweep) {
+        float *tile = reinterpret_cast<float *>(smem + kOffTile) + (grp * 4 + ewarp) * (32 * kTilePitch);
+        const int rows_here = min(32, g.rows_valid - ewarp * 32);
+        const int c = lane & 15, rsel = lane >> 4;  // two rows of 16 columns per store instruction
+        float *orow = g.out + (int64_t)(ewarp * 32 + rsel) * g.F + g.f0 + c;
+        float v[16], ahead[16];
+        tmem_ld16_issue(trow, v);
+        tmem_ld_wait(v);
+        for (int b = 0; b < n_blocks; ++b) {
+            tmem_ld16_issue(trow + (uint32_t)(16 * (b + 1)), ahead);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tile[lane * kTilePitch + i] = v[i] * inv_sum;
+            __syncwarp();
+            float o[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) o[k] = tile[(2 * k + rsel) * kTilePitch + c];
+            const bool col_ok = g.f0 + 16 * b + c < g.f1;
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                if (col_ok && 2 * k + rsel < rows_here) st_stream(orow + (int64_t)(2 * k) * g.F + 16 * b, o[k]);
+            __syncwarp();
+            tmem_ld_wait(ahead);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = ahead[i];
         }
     }
 }
@@ -258,60 +479,32 @@ __device__ __forceinline__ void median_block(const float (&prev)[16], const floa
 // ------------------------------------------------------------------ the kernel
 template <int W>
 __global__ void __launch_bounds__(kThreads, 1)
-capture_tc_kernel(const __grid_constant__ LayerPtrs ptrs, const wca_utt_t *__restrict__ utts, int n_heads,
-                  int lh_count, int tok_blocks, int64_t ld_q, int64_t ld_k, float s, float qk_scale, int raw_logits,
-                  float *__restrict__ ws) {
+capture_tc_kernel(const __grid_constant__ LayerPtrs ptrs, const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
-
-    // ---- tile decode (identical for every CTA of a cluster) ----------------------------
-    const int tile = blockIdx.x / csize;
-    const int tb = tile % tok_blocks;
-    const int lh = (tile / tok_blocks) % lh_count;
-    const int ub = tile / (tok_blocks * lh_count);
-    const wca_utt_t u = utts[ub];
-    const int T = u.n_tokens, F = u.n_frames;
-    const int t0 = tb * kRows;
-    if (t0 >= T) return;
-    const int rows_valid = min(kRows, T - t0);
-    const int layer = lh / n_heads, head = lh % n_heads;
-    const float *qsrc = ptrs.q[layer] + (u.q_row0 + t0) * ld_q + (int64_t)head * kHeadDim;
-    const float *ksrc = ptrs.k[layer] + u.k_row0 * ld_k + (int64_t)head * kHeadDim;
-    float *out = ws + u.ws_off + ((int64_t)lh * T + t0) * F;
-
-    // frame slab of this CTA
-    const int slab = (((F + (int)csize - 1) / (int)csize) + 15) & ~15;
-    const int f0 = (int)crank * slab;
-    const int f1 = min(F, f0 + slab);
-    const int n_own = max(0, f1 - f0);
-    const bool filter = !raw_logits && W > 1 && F > W / 2;  // identity for very short rows, like upstream
-    const int half = filter ? W / 2 : 0;
-    const int m0 = f0 > 0 ? f0 - kHalo : 0;                 // first frame the MMA computes
-    const int mcol0 = f0 > 0 ? 0 : kOwnCol0;                // its TMEM column: frame f sits at column f - f0 + 16
-    const int m1 = n_own > 0 ? min(f1 + kHalo, F) : m0;
-    const int n_mma = m1 - m0;
-    const int n_chunks = (n_mma + kChunk - 1) / kChunk;
-
-    float *smax = reinterpret_cast<float *>(smem + kOffStat);
-    float *ssum = smax + kRows;
-    const uint32_t bar_full0 = smem_u32(smem + kOffBar), bar_full1 = bar_full0 + 8;
-    const uint32_t bar_kfree0 = bar_full0 + 16, bar_kfree1 = bar_full0 + 24, bar_done = bar_full0 + 32;
+    const int cid = blockIdx.x / csize, n_clusters = gridDim.x / csize;
+    const uint32_t bars = smem_u32(smem + kOffBar);
+    auto bar = [&](int which) { return bars + 8u * (uint32_t)which; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kOffTmem);
-    const uint32_t stage0 = smem_u32(smem + kOffStage), stage1 = stage0 + kStageBytes;
 
     // ---- setup ------------------------------------------------------------------------
     if (tid == 0) {
-        mbar_init(bar_full0, 1);
-        mbar_init(bar_full1, 1);
-        mbar_init(bar_kfree0, 1);
-        mbar_init(bar_kfree1, 1);
-        mbar_init(bar_done, 1);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(bar(kStageFull + i), 1);
+            mbar_init(bar(kStageEmpty + i), kSplitThreads);
+        }
+        mbar_init(bar(kAReady), kSplitThreads);
+        mbar_init(bar(kAFree), 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar(kBReady + i), kSplitThreads);
+            mbar_init(bar(kBFree + i), 1);
+            mbar_init(bar(kAccFull + i), 1);
+            mbar_init(bar(kAccEmpty + i), kEpiThreads);
+            mbar_init(bar(kXMax + i), csize);
+            mbar_init(bar(kXSum + i), csize);
+        }
         fence_mbar_init();
-    }
-    if (tid < kRows) {
-        smax[tid] = -INFINITY;
-        ssum[tid] = 0.f;
     }
     if (warp == 0) {
         tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -321,166 +514,131 @@ capture_tc_kernel(const __grid_constant__ LayerPtrs ptrs, const wca_utt_t *__res
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    cluster_sync_all();  // peers' barriers are initialised before anyone arrives remotely
 
-    if (n_own > 0) {
-        // ---- Q: two 64-row halves through the two staging tiles ------------------------
-        if (warp == 4) {
-            producer_load(stage0, qsrc, ld_q, min(rows_valid, kStageRows), bar_full0, lane);
-            producer_load(stage1, qsrc + (int64_t)kStageRows * ld_q, ld_q, max(rows_valid - kStageRows, 0), bar_full1, lane);
+    if (warp == 0) {
+        // ================= TMA producer =================
+        uint32_t n_item = 0;
+        const uint32_t stage0 = smem_u32(smem + kOffStage);
+        for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
+            const Geo g = decode_tile<W>(ptrs, a, tile, crank, csize);
+            if (!g.live || g.n_own == 0) continue;
+            for (int h = 0; h < 2; ++h) {  // Q in two 64-row halves
+                const int nv = min(max(g.rows_valid - h * kStageRows, 0), kStageRows);
+                if (nv == 0) continue;
+                const uint32_t s = n_item % kStages;
+                producer_item(stage0 + s * kStageBytes, bar(kStageFull + s), bar(kStageEmpty + s), n_item,
+                              g.qsrc + (int64_t)h * kStageRows * a.ld_q, a.ld_q, nv, lane);
+                ++n_item;
+            }
+            for (int j = 0; j < g.n_chunks; ++j) {
+                const uint32_t s = n_item % kStages;
+                producer_item(stage0 + s * kStageBytes, bar(kStageFull + s), bar(kStageEmpty + s), n_item,
+                              g.ksrc + (int64_t)(g.m0 + j * kChunk) * a.ld_k, a.ld_k, min(kChunk, g.n_mma - j * kChunk),
+                              lane);
+                ++n_item;
+            }
         }
-        mbar_wait(bar_full0, 0);
-        split_stage(smem + kOffStage, smem + kOffQHi, smem + kOffQLo, kLboQ, 0, s, tid);
-        mbar_wait(bar_full1, 0);
-        split_stage(smem + kOffStage + kStageBytes, smem + kOffQHi, smem + kOffQLo, kLboQ, kStageRows, s, tid);
-        __syncthreads();
-
-        // ---- K chunks: TMA(j+2) | split(j+1) | MMA(j) ----------------------------------
-        auto chunk_rows = [&](int j) { return min(kChunk, n_mma - j * kChunk); };
-        if (warp == 4) {
-            producer_load(stage0, ksrc + (int64_t)m0 * ld_k, ld_k, chunk_rows(0), bar_full0, lane);
-            if (n_chunks > 1)
-                producer_load(stage1, ksrc + (int64_t)(m0 + kChunk) * ld_k, ld_k, chunk_rows(1), bar_full1, lane);
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t n_tile = 0, n_chunk = 0, acc_use[2] = {0, 0}, it = 0;
+            const uint32_t a_hi = smem_u32(smem + kOffQHi), a_lo = smem_u32(smem + kOffQLo);
+            for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
+                const Geo g = decode_tile<W>(ptrs, a, tile, crank, csize);
+                if (!g.live) continue;
+                const uint32_t buf = it & 1u;
+                ++it;
+                if (g.n_own == 0) continue;
+                mbar_wait(bar(kAccEmpty + buf), (acc_use[buf] & 1u) ^ 1u);  // epilogue drained this accumulator
+                ++acc_use[buf];
+                mbar_wait(bar(kAReady), n_tile & 1u);
+                ++n_tile;
+                for (int j = 0; j < g.n_chunks; ++j) {
+                    const uint32_t kb = n_chunk & 1u;
+                    mbar_wait(bar(kBReady + kb), (n_chunk >> 1) & 1u);
+                    ++n_chunk;
+                    tc_fence_after();
+                    const int n_cols = (min(kChunk, g.n_mma - j * kChunk) + 15) & ~15;  // UMMA N: multiple of 16
+                    const uint32_t idesc = instr_desc_tf32(kRows, n_cols);
+                    const uint32_t d = tmem_base + buf * kAccCols + (uint32_t)(g.mcol0 + j * kChunk);
+                    const uint32_t b_hi = smem_u32(smem + kOffKHi) + kb * kKSplitBytes;
+                    const uint32_t b_lo = smem_u32(smem + kOffKLo) + kb * kKSplitBytes;
+                    // small terms first: lo*hi, hi*lo, then hi*hi
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t pa = pass == 0 ? a_lo : a_hi;
+                        const uint32_t pb = pass == 1 ? b_lo : b_hi;
+#pragma unroll
+                        for (int ks = 0; ks < kHeadDim / 8; ++ks)  // K = 8 tf32 (two 16-byte k-chunks) per instruction
+                            umma_tf32(d, smem_desc(pa + ks * 2 * kLboQ, kLboQ, kSbo),
+                                      smem_desc(pb + ks * 2 * kLboK, kLboK, kSbo), idesc, (pass | ks) != 0);
+                    }
+                    umma_commit(bar(kBFree + kb));
+                }
+                umma_commit(bar(kAFree));
+                umma_commit(bar(kAccFull + buf));
+            }
         }
-        for (int j = 0; j < n_chunks; ++j) {
-            const int sidx = j & 1;
-            const uint32_t bar_full = sidx ? bar_full1 : bar_full0;
-            const uint32_t bar_kfree = sidx ? bar_kfree1 : bar_kfree0;
-            mbar_wait(bar_full, (uint32_t)(1 + (j >> 1)) & 1u);             // completion #1+(j>>1) of this stage
-            if (j >= 2) mbar_wait(bar_kfree, (uint32_t)((j >> 1) - 1) & 1u);  // MMA j-2 released this K buffer
-            unsigned char *khi = smem + kOffKHi + sidx * kKSplitBytes;
-            unsigned char *klo = smem + kOffKLo + sidx * kKSplitBytes;
-            split_stage(smem + kOffStage + sidx * kStageBytes, khi, klo, kLboK, 0, s, tid);
-            tc_fence_before();
-            __syncthreads();  // splits visible, staging tile `sidx` free again
-            if (warp == 4 && j + 2 < n_chunks)
-                producer_load(sidx ? stage1 : stage0, ksrc + (int64_t)(m0 + (j + 2) * kChunk) * ld_k, ld_k,
-                              chunk_rows(j + 2), bar_full, lane);
-            if (tid == 32 * 5) {  // one thread issues the MMAs of this chunk
+        __syncwarp();
+    } else if (warp >= 4 && warp < 8) {
+        // ================= operand splitters =================
+        const int t = tid - 4 * 32;
+        uint32_t n_item = 0, n_tile = 0, n_chunk = 0;
+        for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
+            const Geo g = decode_tile<W>(ptrs, a, tile, crank, csize);
+            if (!g.live || g.n_own == 0) continue;
+            mbar_wait(bar(kAFree), (n_tile & 1u) ^ 1u);  // MMAs of the previous tile no longer read Q
+            ++n_tile;
+            for (int h = 0; h < 2; ++h) {
+                if (g.rows_valid - h * kStageRows <= 0) continue;
+                const uint32_t s = n_item % kStages;
+                mbar_wait(bar(kStageFull + s), (n_item / kStages) & 1u);
+                split_stage(smem + kOffStage + s * kStageBytes, smem + kOffQHi, smem + kOffQLo, kLboQ, h * kStageRows,
+                            a.s, t);
+                mbar_arrive(bar(kStageEmpty + s));
+                ++n_item;
+            }
+            mbar_arrive(bar(kAReady));
+            for (int j = 0; j < g.n_chunks; ++j) {
+                const uint32_t s = n_item % kStages, kb = n_chunk & 1u;
+                mbar_wait(bar(kBFree + kb), ((n_chunk >> 1) & 1u) ^ 1u);  // MMA released this K buffer
+                mbar_wait(bar(kStageFull + s), (n_item / kStages) & 1u);
+                split_stage(smem + kOffStage + s * kStageBytes, smem + kOffKHi + kb * kKSplitBytes,
+                            smem + kOffKLo + kb * kKSplitBytes, kLboK, 0, a.s, t);
+                mbar_arrive(bar(kStageEmpty + s));
+                mbar_arrive(bar(kBReady + kb));
+                ++n_item;
+                ++n_chunk;
+            }
+        }
+    } else if (warp >= 8) {
+        // ================= epilogue warpgroups (A: even tiles, B: odd tiles) =================
+        const int grp = (warp - 8) >> 2, ewarp = warp & 3;
+        uint32_t it = 0, acc_use = 0, n_x = 0;
+        for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
+            const Geo g = decode_tile<W>(ptrs, a, tile, crank, csize);
+            if (!g.live) continue;
+            const bool mine = (it & 1u) == (uint32_t)grp;
+            ++it;
+            if (!mine) continue;
+            if (g.n_own > 0) {
+                mbar_wait(bar(kAccFull + grp), acc_use & 1u);
                 tc_fence_after();
-                const int n_cols = (chunk_rows(j) + 15) & ~15;  // UMMA N: multiple of 16 for M = 128
-                const uint32_t idesc = instr_desc_tf32(kRows, n_cols);
-                const uint32_t d = tmem_base + (uint32_t)(mcol0 + j * kChunk);
-                const uint32_t a_hi = smem_u32(smem + kOffQHi), a_lo = smem_u32(smem + kOffQLo);
-                const uint32_t b_hi = smem_u32(khi), b_lo = smem_u32(klo);
-                // small terms first: lo*hi, hi*lo, then hi*hi
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t a = pass == 0 ? a_lo : a_hi;
-                    const uint32_t b = pass == 1 ? b_lo : b_hi;
-#pragma unroll
-                    for (int ks = 0; ks < kHeadDim / 8; ++ks)  // K = 8 tf32 (two 16-byte k-chunks) per instruction
-                        umma_tf32(d, smem_desc(a + ks * 2 * kLboQ, kLboQ, kSbo), smem_desc(b + ks * 2 * kLboK, kLboK, kSbo),
-                                  idesc, (pass | ks) != 0);
-                }
-                umma_commit(bar_kfree);
-                if (j == n_chunks - 1) umma_commit(bar_done);
             }
-        }
-        mbar_wait(bar_done, 0);
-        tc_fence_after();
-    }
-    __syncthreads();
-
-    // ---- epilogue: warps 0-3, thread <-> token row ----------------------------------------
-    const int row = tid;  // valid for tid < 128
-    const bool epi_warp = warp < 4;
-    const bool row_ok = epi_warp && row < rows_valid;
-    const bool warp_has_rows = epi_warp && (warp * 32 < rows_valid) && n_own > 0;
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);  // lane quarter of this warp
-    const int n_blocks = (n_own + 15) >> 4;
-
-    if (warp_has_rows && filter) {
-        // materialise the reflect padding inside TMEM: frame -i <- frame i, frame F-1+i <- frame F-1-i
-        if (f0 == 0)
-            for (int i = 1; i <= half; ++i) tmem_st1(trow + (uint32_t)(kOwnCol0 - i), tmem_ld1(trow + (uint32_t)(kOwnCol0 + i)));
-        for (int g = max(F, f1); g < f1 + half; ++g)
-            tmem_st1(trow + (uint32_t)(g - f0 + kOwnCol0), tmem_ld1(trow + (uint32_t)(2 * (F - 1) - g - f0 + kOwnCol0)));
-        tmem_wait_st();
-    }
-
-    float row_max = -INFINITY;
-    if (warp_has_rows && !raw_logits) {
-        // sweep A: median filter (in place), * qk_scale, running max
-        float prev[16], cur[16], next[16], med[16];
-        tmem_ld16(trow + (uint32_t)(kOwnCol0 - 16), prev);
-        tmem_ld16(trow + (uint32_t)kOwnCol0, cur);
-        for (int b = 0; b < n_blocks; ++b) {
-            tmem_ld16(trow + (uint32_t)(kOwnCol0 + 16 * (b + 1)), next);
-            if (filter) median_block<W>(prev, cur, next, med);
-            else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) med[i] = cur[i];
+            epilogue_tile<W>(g, a, smem, tmem_base + (uint32_t)grp * kAccCols, grp, ewarp, lane, csize, n_x & 1u);
+            ++n_x;
+            if (g.n_own > 0) {
+                tc_fence_before();
+                mbar_arrive(bar(kAccEmpty + grp));
+                ++acc_use;
             }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                med[i] *= qk_scale;
-                if (16 * b + i < n_own) row_max = fmaxf(row_max, med[i]);
-            }
-            tmem_st16(trow + (uint32_t)(kOwnCol0 + 16 * b), med);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                prev[i] = cur[i];
-                cur[i] = next[i];
-            }
-        }
-        tmem_wait_st();
-        if (row_ok) smax[row] = row_max;
-    }
-    float inv_sum = 1.f;
-    if (!raw_logits) {
-        cluster_sync_all();
-        float gmax = -INFINITY;
-        if (row_ok)
-            for (uint32_t r = 0; r < csize; ++r) gmax = fmaxf(gmax, ld_dsmem_f32(&smax[row], r));
-        // sweep B: e = exp(x - max) in place, running sum
-        float row_sum = 0.f;
-        if (warp_has_rows) {
-            const float kLog2e = 1.4426950408889634f;
-            const float shift = gmax * kLog2e;
-            float v[16];
-            for (int b = 0; b < n_blocks; ++b) {
-                tmem_ld16(trow + (uint32_t)(kOwnCol0 + 16 * b), v);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    v[i] = exp2f(fmaf(v[i], kLog2e, -shift));
-                    if (16 * b + i < n_own) row_sum += v[i];
-                }
-                tmem_st16(trow + (uint32_t)(kOwnCol0 + 16 * b), v);
-            }
-            tmem_wait_st();
-            if (row_ok) ssum[row] = row_sum;
-        }
-        cluster_sync_all();
-        float gsum = 0.f;
-        if (row_ok)
-            for (uint32_t r = 0; r < csize; ++r) gsum += ld_dsmem_f32(&ssum[row], r);
-        inv_sum = 1.f / gsum;
-    }
-
-    // sweep C: normalise, transpose 32x16 blocks through shared memory, coalesced row stores
-    if (warp_has_rows) {
-        float *tile = reinterpret_cast<float *>(smem + kOffStage) + warp * (32 * kTilePitch);
-        const int rows_here = min(32, rows_valid - warp * 32);
-        float v[16];
-        for (int b = 0; b < n_blocks; ++b) {
-            tmem_ld16(trow + (uint32_t)(kOwnCol0 + 16 * b), v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) tile[lane * kTilePitch + i] = v[i] * inv_sum;
-            __syncwarp();
-            // lane -> (row parity, column): two rows of 16 columns per store instruction
-            const int c = lane & 15, rsel = lane >> 4;
-            const int f = f0 + 16 * b + c;
-#pragma unroll 4
-            for (int rr = 0; rr < 32; rr += 2) {
-                const int r = rr + rsel;
-                if (r < rows_here && f < f1) st_stream(out + (int64_t)(warp * 32 + r) * F + f, tile[r * kTilePitch + c]);
-            }
-            __syncwarp();
         }
     }
 
     // ---- teardown: nobody leaves while a peer may still read our statistics ----------------
     tc_fence_before();
+    __syncthreads();
     cluster_sync_all();
     if (warp == 0) {
         tc_fence_after();
@@ -499,7 +657,6 @@ bool capture_tc_supported(int max_tokens, int max_frames, int medfilt_width) {
 int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_layers, int n_layers, int n_heads,
                       int64_t ld_q, int64_t ld_k, const wca_utt_t *d_utts, int n_utts, int max_tokens, int max_frames,
                       int medfilt_width, float qk_scale, float *d_ws, unsigned flags, int sm_count, cudaStream_t stream) {
-    (void)sm_count;
     LayerPtrs p;
     for (int l = 0; l < WCA_MAX_LAYERS; ++l) {
         p.q[l] = l < n_layers ? h_q_layers[l] : nullptr;
@@ -510,16 +667,29 @@ int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_la
     const int tok_blocks = (max_tokens + tc::kRows - 1) / tc::kRows;
     const int lh_count = n_layers * n_heads;
     const long long tiles = (long long)n_utts * lh_count * tok_blocks;
-    if (tiles * csize > 0x7fffffffLL) {
-        set_error("capture_tc: grid of %lld CTAs too large", tiles * csize);
+    if (tiles > 0x7fffffffLL) {
+        set_error("capture_tc: %lld tiles exceed the tile index range", tiles);
         return WCA_ERR_UNSUPPORTED;
     }
-    const float s = (float)0.35355339059327373;  // 64 ** -0.25 as the reference's fp32 scalar
-    const int raw = (flags & WCA_CAPTURE_RAW_LOGITS) ? 1 : 0;
-    const int width = raw ? 1 : medfilt_width;
+    tc::KernelArgs a;
+    a.utts = d_utts;
+    a.ws = d_ws;
+    a.ld_q = ld_q;
+    a.ld_k = ld_k;
+    a.n_heads = n_heads;
+    a.lh_count = lh_count;
+    a.tok_blocks = tok_blocks;
+    a.n_tiles = (int)tiles;
+    a.s = (float)0.35355339059327373;  // 64 ** -0.25 as the reference's fp32 scalar
+    a.qk_scale = qk_scale;
+    a.raw_logits = (flags & WCA_CAPTURE_RAW_LOGITS) ? 1 : 0;
+    const int width = a.raw_logits ? 1 : medfilt_width;
 
+    long long clusters = sm_count / csize;  // one persistent CTA per SM
+    if (clusters > tiles) clusters = tiles;
+    if (clusters < 1) clusters = 1;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(tiles * csize));
+    cfg.gridDim = dim3((unsigned)(clusters * csize));
     cfg.blockDim = dim3(tc::kThreads);
     cfg.dynamicSmemBytes = tc::kSmemBytes;
     cfg.stream = stream;
@@ -531,12 +701,11 @@ int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_la
     cfg.attrs = attr;
     cfg.numAttrs = 1;
 
-#define WCA_GO(Wv)                                                                                                  \
-    do {                                                                                                            \
-        WCA_CUDA(cudaFuncSetAttribute(tc::capture_tc_kernel<Wv>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                      tc::kSmemBytes));                                                             \
-        WCA_CUDA(cudaLaunchKernelEx(&cfg, tc::capture_tc_kernel<Wv>, p, d_utts, n_heads, lh_count, tok_blocks, ld_q, \
-                                    ld_k, s, qk_scale, raw, d_ws));                                                 \
+#define WCA_GO(Wv)                                                                                              \
+    do {                                                                                                        \
+        WCA_CUDA(cudaFuncSetAttribute(tc::capture_tc_kernel<Wv>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                      tc::kSmemBytes));                                                         \
+        WCA_CUDA(cudaLaunchKernelEx(&cfg, tc::capture_tc_kernel<Wv>, p, a));                                    \
     } while (0)
     switch (width) {
         case 1: WCA_GO(1); break;
