@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define WCA_ABI_VERSION 1
+#define WCA_ABI_VERSION 2
 #define WCA_MAX_LAYERS 64      /* large-v3 has 32 */
 #define WCA_MAX_MEDFILT 31     /* odd widths 1..31 */
 #define WCA_TOKENS_PER_SECOND 50.0 /* whisper.audio.TOKENS_PER_SECOND, timing.py:10,111 */
@@ -82,14 +82,15 @@ WCA_API int wca_device_info(int *sm_count, int *compute_capability);
  * then (unless WCA_CAPTURE_RAW_LOGITS) median filter of odd `medfilt_width` along f with
  * reflect padding inside [0, n_frames), times `qk_scale`, softmax over f.
  * h_q_layers / h_k_layers: HOST arrays of L device pointers; layer l's Q is a row-major
- * matrix with leading dimension ld_q floats whose row (q_row0 + t) holds token t, columns
- * [h*Dh, (h+1)*Dh) belong to head h; likewise K with ld_k and frame rows.
+ * matrix of q_rows rows with leading dimension ld_q floats whose row (q_row0 + t) holds
+ * token t, columns [h*Dh, (h+1)*Dh) belong to head h; likewise K with k_rows, ld_k and
+ * frame rows (the row counts bound the TMA tensor maps: rows past them read as zero).
  * Output: d_ws + ws_off, layout (L, H, T, F) fp32, exactly what get_attentions returns. */
 #define WCA_CAPTURE_RAW_LOGITS 1u
 #define WCA_CAPTURE_FORCE_SIMT 2u /* use the CUDA-core kernel instead of tcgen05 (test cross-check) */
 WCA_API int wca_capture_attention(const float *const *h_q_layers, const float *const *h_k_layers, int n_layers,
                           int n_heads_per_layer, int head_dim, int64_t ld_q, int64_t ld_k,
-                          const wca_utt_t *d_utts, int n_utts, int max_tokens, int max_frames,
+                          int64_t q_rows, int64_t k_rows, const wca_utt_t *d_utts, int n_utts, int max_tokens, int max_frames,
                           int medfilt_width, float qk_scale, float *d_ws, unsigned flags,
                           wca_stream_t stream);
 

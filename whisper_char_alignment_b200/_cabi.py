@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libwca_b200.so")
 WCA_CAPTURE_RAW_LOGITS = 1
 WCA_CAPTURE_FORCE_SIMT = 2
 WCA_MAX_LAYERS = 64
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = (
     "wca_abi_version", "wca_last_error", "wca_launch_count", "wca_device_info", "wca_capture_attention", "wca_medfilt_softmax",
@@ -70,7 +70,7 @@ def load() -> ctypes.CDLL:
     lib.wca_last_error.restype = ctypes.c_char_p
     lib.wca_launch_count.restype = ctypes.c_uint64
     lib.wca_device_info.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(i32)]
-    lib.wca_capture_attention.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, i32, i32, i32, i32, f32, vp,
+    lib.wca_capture_attention.argtypes = [vp, vp, i32, i32, i32, i64, i64, i64, i64, vp, i32, i32, i32, i32, f32, vp,
                                           ctypes.c_uint, vp]
     lib.wca_medfilt_softmax.argtypes = [vp, i64, i64, i32, i32, f32, vp, vp]
     lib.wca_head_scores.argtypes = [vp, vp, i32, i32, i32, i32, f32, f32, f32, vp, vp]
@@ -190,9 +190,15 @@ def capture_attention(q_layers: Sequence[torch.Tensor], k_layers: Sequence[torch
     qp = (ctypes.c_void_p * n_layers)(*[_dev_ptr(t, torch.float32, "Q") for t in q_layers])
     kp = (ctypes.c_void_p * n_layers)(*[_dev_ptr(t, torch.float32, "K") for t in k_layers])
     head_dim = 64
+    q_rows = q_layers[0].numel() // ld_q
+    k_rows = k_layers[0].numel() // ld_k
+    for q, k in zip(q_layers, k_layers):
+        if q.numel() != q_rows * ld_q or k.numel() != k_rows * ld_k:
+            raise WcaError("every layer's Q (and K) must have the same shape")
     with _timed("wca_capture_attention"):
         _check(
-            load().wca_capture_attention(qp, kp, n_layers, n_heads, head_dim, ld_q, ld_k, _dev_ptr(d_utts), n_utts,
+            load().wca_capture_attention(qp, kp, n_layers, n_heads, head_dim, ld_q, ld_k, q_rows, k_rows,
+                                         _dev_ptr(d_utts), n_utts,
                                          max_tokens, max_frames, medfilt_width, float(qk_scale),
                                          _dev_ptr(ws, torch.float32, "ws"), flags, _stream()),
             "wca_capture_attention",

@@ -40,8 +40,8 @@ static int device_sm_count(int *sms, int *cc) {
 // kernels (defined in the other translation units)
 int launch_capture_logits_simt(const float *const *, const float *const *, int, int, int64_t, int64_t,
                                const wca_utt_t *, int, int, float *, cudaStream_t);
-int launch_capture_tc(const float *const *, const float *const *, int, int, int64_t, int64_t, const wca_utt_t *, int,
-                      int, int, int, float, float *, unsigned, int, cudaStream_t);
+int launch_capture_tc(const float *const *, const float *const *, int, int, int64_t, int64_t, int64_t, int64_t,
+                      const wca_utt_t *, int, int, int, int, float, float *, unsigned, int, cudaStream_t);
 bool capture_tc_supported(int max_tokens, int max_frames, int medfilt_width);
 int launch_medfilt_softmax_rows(const float *, int64_t, int64_t, int, int, float, float *, int, cudaStream_t);
 int launch_medfilt_softmax_batched(float *, const wca_utt_t *, int, int, int, int, int, float, int, cudaStream_t);
@@ -69,8 +69,8 @@ uint64_t wca_launch_count(void) { return g_launches; }
 int wca_device_info(int *sm_count, int *compute_capability) { return device_sm_count(sm_count, compute_capability); }
 
 int wca_capture_attention(const float *const *h_q_layers, const float *const *h_k_layers, int n_layers,
-                          int n_heads_per_layer, int head_dim, int64_t ld_q, int64_t ld_k, const wca_utt_t *d_utts,
-                          int n_utts, int max_tokens, int max_frames, int medfilt_width, float qk_scale, float *d_ws,
+                          int n_heads_per_layer, int head_dim, int64_t ld_q, int64_t ld_k, int64_t q_rows,
+                          int64_t k_rows, const wca_utt_t *d_utts, int n_utts, int max_tokens, int max_frames, int medfilt_width, float qk_scale, float *d_ws,
                           unsigned flags, wca_stream_t stream) {
     WCA_CHECK_ARG(h_q_layers && h_k_layers && d_utts && d_ws, "wca_capture_attention: null pointer");
     WCA_CHECK_ARG(n_layers >= 1 && n_layers <= WCA_MAX_LAYERS, "wca_capture_attention: n_layers=%d not in [1,%d]",
@@ -85,6 +85,8 @@ int wca_capture_attention(const float *const *h_q_layers, const float *const *h_
                       ld_q % 4 == 0 && ld_k % 4 == 0,
                   "wca_capture_attention: leading dimensions (%lld, %lld) must cover H*Dh and be multiples of 4",
                   (long long)ld_q, (long long)ld_k);
+    WCA_CHECK_ARG(q_rows >= 1 && k_rows >= 1 && q_rows < (1ll << 31) && k_rows < (1ll << 31),
+                  "wca_capture_attention: row counts (%lld, %lld) out of range", (long long)q_rows, (long long)k_rows);
     WCA_CHECK_ARG(n_utts >= 0 && n_utts <= 65535 && max_tokens >= 1 && max_frames >= 1,
                   "wca_capture_attention: bad batch geometry (%d utts, %d tokens, %d frames)", n_utts, max_tokens,
                   max_frames);
@@ -107,7 +109,7 @@ int wca_capture_attention(const float *const *h_q_layers, const float *const *h_
             set_error("wca_capture_attention: tcgen05 path needs compute capability 10.x, device is %d", cc);
             return WCA_ERR_NO_DEVICE;
         }
-        return launch_capture_tc(h_q_layers, h_k_layers, n_layers, n_heads_per_layer, ld_q, ld_k, d_utts, n_utts,
+        return launch_capture_tc(h_q_layers, h_k_layers, n_layers, n_heads_per_layer, ld_q, ld_k, q_rows, k_rows, d_utts, n_utts,
                                  max_tokens, max_frames, medfilt_width, qk_scale, d_ws, flags, sms, st);
     }
     rc = launch_capture_logits_simt(h_q_layers, h_k_layers, n_layers, n_heads_per_layer, ld_q, ld_k, d_utts, n_utts,

@@ -20,14 +20,21 @@
 //   fp32 in, fp32-grade out on the tensor pipe: operands are split v = hi + lo (hi, lo
 //               rounded to tf32) and lo*hi + hi*lo + hi*hi is accumulated: 3 x 8
 //               tcgen05.mma kind::tf32 per 64-frame chunk, error ~1e-6 relative;
-//   TMA     : Q / K head rows (256 B) arrive by cp.async.bulk on mbarriers into a 3-stage
-//               staging ring; splitter warps rewrite them into the no-swizzle K-major UMMA
-//               layout [k-chunk][8-row group][8 rows][16 B].
+//   TMA     : Q / K tiles arrive as 2-D tensor-map boxes (cp.async.bulk.tensor.2d, 64 rows x
+//               32 floats, 128-byte swizzle, two boxes per 64-row stage) on mbarriers into a
+//               4-stage staging ring; splitter warps rewrite them into the no-swizzle K-major
+//               UMMA layout [k-chunk][8-row group][8 rows][16 B].  (Row-granular
+//               cp.async.bulk copies measured ~75 cycles each in the TMA unit and starved the
+//               pipeline: profiles/r01_capture_tc_v2_*.)
 //
 // Roles of the 16 warps of a CTA (one persistent CTA per SM, static tile schedule):
 //   warp 0      TMA producer            warp 1      MMA issuer (one thread)
 //   warps 4-7   operand splitters       warps 8-11 / 12-15   epilogue warpgroups A / B,
 //                                       alternating tiles (accumulator i & 1)
+#include <cuda.h>  // CUtensorMap and its enums only; the encoder is fetched from the driver at run time
+
+#include <cstring>
+
 #include "common.cuh"
 
 namespace wca {
@@ -42,10 +49,11 @@ constexpr int kAccCols = 256;        // columns per accumulator
 constexpr int kMaxOwn = kAccCols - 2 * kHalo;   // 224 own frames per CTA and tile
 constexpr int kTmemCols = 512;
 constexpr int kRowBytes = kHeadDim * 4;          // 256
-constexpr int kStagePitch = kRowBytes + 16;      // padded: conflict-free 16-byte column reads
 constexpr int kStageRows = 64;
-constexpr int kStageBytes = kStageRows * kStagePitch;   // 17408
-constexpr int kStages = 3;
+constexpr int kBoxCols = 32;                       // floats per TMA box row: 128 B, the swizzle span
+constexpr int kBoxBytes = kStageRows * kBoxCols * 4;     // 8192
+constexpr int kStageBytes = 2 * kBoxBytes;               // 16384: [column half][64 rows][128 B swizzled]
+constexpr int kStages = 4;
 constexpr int kQSplitBytes = kRows * kRowBytes;         // 32768 per hi / lo
 constexpr int kKSplitBytes = kChunk * kRowBytes;        // 16384 per hi / lo per buffer
 constexpr uint32_t kLboQ = kRows * 16;   // bytes between consecutive 16-byte k-chunks (A operand)
@@ -145,11 +153,14 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     for (uint32_t spins = 0; !mbar_try_wait_cluster(bar, parity); ++spins)
         if (spins > (1u << 24)) __trap();
 }
-// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
-__device__ __forceinline__ void tma_load_row(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
+// TMA tensor-map box load global -> shared, completion signalled on an mbarrier (SASS: UTMALDG).
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap *map, int col, int row, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+                     "r"(dst), "l"(map), "r"(col), "r"(row), "r"(bar)
                  : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_map(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -243,10 +254,14 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 // ------------------------------------------------------------------ tile geometry
+struct TensorMaps {
+    CUtensorMap q[WCA_MAX_LAYERS];  // (rows, H*64) fp32 matrices, box 64 rows x 32 floats, 128B swizzle
+    CUtensorMap k[WCA_MAX_LAYERS];
+};
+
 struct KernelArgs {
     const wca_utt_t *utts;
     float *ws;
-    int64_t ld_q, ld_k;
     int n_heads, lh_count, tok_blocks, n_tiles;
     float s, qk_scale;
     int raw_logits;
@@ -259,13 +274,13 @@ struct Geo {
     int half;                // filter half-width actually applied (0: identity)
     int m0, mcol0, n_mma;    // first frame / accumulator column / frame count the MMA computes
     int n_chunks;
-    const float *qsrc, *ksrc;
+    int layer, col0;         // decoder layer and first float column of the head
+    int qrow0, krow0;        // first Q row of the tile / first K row of the utterance
     float *out;              // row 0 of this tile, frame 0
 };
 
 template <int W>
-__device__ __forceinline__ Geo decode_tile(const LayerPtrs &ptrs, const KernelArgs &a, int tile, uint32_t crank,
-                                           uint32_t csize) {
+__device__ __forceinline__ Geo decode_tile(const KernelArgs &a, int tile, uint32_t crank, uint32_t csize) {
     Geo g;
     const int tb = tile % a.tok_blocks;
     const int lh = (tile / a.tok_blocks) % a.lh_count;
@@ -276,9 +291,10 @@ __device__ __forceinline__ Geo decode_tile(const LayerPtrs &ptrs, const KernelAr
     const int t0 = tb * kRows;
     g.live = t0 < g.T;
     g.rows_valid = min(kRows, g.T - t0);
-    const int layer = lh / a.n_heads, head = lh % a.n_heads;
-    g.qsrc = ptrs.q[layer] + (u.q_row0 + t0) * a.ld_q + (int64_t)head * kHeadDim;
-    g.ksrc = ptrs.k[layer] + u.k_row0 * a.ld_k + (int64_t)head * kHeadDim;
+    g.layer = lh / a.n_heads;
+    g.col0 = (lh % a.n_heads) * kHeadDim;
+    g.qrow0 = (int)u.q_row0 + t0;
+    g.krow0 = (int)u.k_row0;
     g.out = a.ws + u.ws_off + ((int64_t)lh * g.T + t0) * g.F;
     const int slab = (((g.F + (int)csize - 1) / (int)csize) + 15) & ~15;
     g.f0 = (int)crank * slab;
@@ -294,13 +310,16 @@ __device__ __forceinline__ Geo decode_tile(const LayerPtrs &ptrs, const KernelAr
 }
 
 // ------------------------------------------------------------------ role bodies
+// One elected lane arms the stage barrier and issues the two column-half boxes of a 64-row tile.
 __device__ __forceinline__ void producer_item(uint32_t stage, uint32_t bar_full, uint32_t bar_empty, uint32_t n_item,
-                                              const float *src, int64_t ld, int n_valid, int lane) {
+                                              const CUtensorMap *map, int col0, int row0, int lane) {
     mbar_wait(bar_empty, ((n_item / kStages) & 1u) ^ 1u);  // first lap passes immediately
-    if (lane == 0) mbar_expect_tx(bar_full, (uint32_t)n_valid * kRowBytes);
+    if (lane == 0) {
+        mbar_expect_tx(bar_full, kStageBytes);  // boxes are always full: rows past the matrix end read as zero
+        tma_load_box(stage, map, col0, row0, bar_full);
+        tma_load_box(stage + kBoxBytes, map, col0 + kBoxCols, row0, bar_full);
+    }
     __syncwarp();
-    for (int r = lane; r < n_valid; r += kWarp)
-        tma_load_row(stage + r * kStagePitch, src + (int64_t)r * ld, kRowBytes, bar_full);
 }
 
 // 128 splitter threads: staging tile (64 rows) -> scaled hi / lo parts in UMMA no-swizzle layout.
@@ -310,7 +329,9 @@ __device__ __forceinline__ void split_stage(const unsigned char *stage, unsigned
     for (int it = 0; it < (kStageRows * 16) / kSplitThreads; ++it) {
         const int e = it * kSplitThreads + t;
         const int row = e & (kStageRows - 1), ch = e >> 6;
-        const float4 v = *reinterpret_cast<const float4 *>(stage + row * kStagePitch + ch * 16);
+        // 128-byte swizzle of the TMA box: 16-byte chunk c of row r sits at chunk position c ^ (r & 7)
+        const float4 v = *reinterpret_cast<const float4 *>(stage + (ch >> 3) * kBoxBytes + row * 128 +
+                                                           (((ch & 7) ^ (row & 7)) << 4));
         const float x[4] = {v.x * s, v.y * s, v.z * s, v.w * s};
         float h[4], l[4];
 #pragma unroll
@@ -479,7 +500,7 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
 // ------------------------------------------------------------------ the kernel
 template <int W>
 __global__ void __launch_bounds__(kThreads, 1)
-capture_tc_kernel(const __grid_constant__ LayerPtrs ptrs, const __grid_constant__ KernelArgs a) {
+capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
@@ -521,21 +542,19 @@ capture_tc_kernel(const __grid_constant__ LayerPtrs ptrs, const __grid_constant_
         uint32_t n_item = 0;
         const uint32_t stage0 = smem_u32(smem + kOffStage);
         for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
-            const Geo g = decode_tile<W>(ptrs, a, tile, crank, csize);
+            const Geo g = decode_tile<W>(a, tile, crank, csize);
             if (!g.live || g.n_own == 0) continue;
             for (int h = 0; h < 2; ++h) {  // Q in two 64-row halves
-                const int nv = min(max(g.rows_valid - h * kStageRows, 0), kStageRows);
-                if (nv == 0) continue;
+                if (g.rows_valid - h * kStageRows <= 0) continue;
                 const uint32_t s = n_item % kStages;
                 producer_item(stage0 + s * kStageBytes, bar(kStageFull + s), bar(kStageEmpty + s), n_item,
-                              g.qsrc + (int64_t)h * kStageRows * a.ld_q, a.ld_q, nv, lane);
+                              &maps.q[g.layer], g.col0, g.qrow0 + h * kStageRows, lane);
                 ++n_item;
             }
             for (int j = 0; j < g.n_chunks; ++j) {
                 const uint32_t s = n_item % kStages;
                 producer_item(stage0 + s * kStageBytes, bar(kStageFull + s), bar(kStageEmpty + s), n_item,
-                              g.ksrc + (int64_t)(g.m0 + j * kChunk) * a.ld_k, a.ld_k, min(kChunk, g.n_mma - j * kChunk),
-                              lane);
+                              &maps.k[g.layer], g.col0, g.krow0 + g.m0 + j * kChunk, lane);
                 ++n_item;
             }
         }
@@ -545,7 +564,7 @@ capture_tc_kernel(const __grid_constant__ LayerPtrs ptrs, const __grid_constant_
             uint32_t n_tile = 0, n_chunk = 0, acc_use[2] = {0, 0}, it = 0;
             const uint32_t a_hi = smem_u32(smem + kOffQHi), a_lo = smem_u32(smem + kOffQLo);
             for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
-                const Geo g = decode_tile<W>(ptrs, a, tile, crank, csize);
+                const Geo g = decode_tile<W>(a, tile, crank, csize);
                 if (!g.live) continue;
                 const uint32_t buf = it & 1u;
                 ++it;
@@ -586,7 +605,7 @@ capture_tc_kernel(const __grid_constant__ LayerPtrs ptrs, const __grid_constant_
         const int t = tid - 4 * 32;
         uint32_t n_item = 0, n_tile = 0, n_chunk = 0;
         for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
-            const Geo g = decode_tile<W>(ptrs, a, tile, crank, csize);
+            const Geo g = decode_tile<W>(a, tile, crank, csize);
             if (!g.live || g.n_own == 0) continue;
             mbar_wait(bar(kAFree), (n_tile & 1u) ^ 1u);  // MMAs of the previous tile no longer read Q
             ++n_tile;
@@ -617,7 +636,7 @@ capture_tc_kernel(const __grid_constant__ LayerPtrs ptrs, const __grid_constant_
         const int grp = (warp - 8) >> 2, ewarp = warp & 3;
         uint32_t it = 0, acc_use = 0, n_x = 0;
         for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
-            const Geo g = decode_tile<W>(ptrs, a, tile, crank, csize);
+            const Geo g = decode_tile<W>(a, tile, crank, csize);
             if (!g.live) continue;
             const bool mine = (it & 1u) == (uint32_t)grp;
             ++it;
@@ -654,13 +673,48 @@ bool capture_tc_supported(int max_tokens, int max_frames, int medfilt_width) {
     return width_ok && max_frames <= 8 * tc::kMaxOwn;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_map(EncodeTiledFn encode, CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int64_t ld) {
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::kBoxCols, (cuuint32_t)tc::kStageRows};
+    const cuuint32_t elem[2] = {1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, elem,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %lld, cols %lld, ld %lld)", (int)r, (long long)rows,
+                  (long long)cols, (long long)ld);
+        return WCA_ERR_CUDA;
+    }
+    return WCA_OK;
+}
+
 int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_layers, int n_layers, int n_heads,
-                      int64_t ld_q, int64_t ld_k, const wca_utt_t *d_utts, int n_utts, int max_tokens, int max_frames,
-                      int medfilt_width, float qk_scale, float *d_ws, unsigned flags, int sm_count, cudaStream_t stream) {
-    LayerPtrs p;
-    for (int l = 0; l < WCA_MAX_LAYERS; ++l) {
-        p.q[l] = l < n_layers ? h_q_layers[l] : nullptr;
-        p.k[l] = l < n_layers ? h_k_layers[l] : nullptr;
+                      int64_t ld_q, int64_t ld_k, int64_t q_rows, int64_t k_rows, const wca_utt_t *d_utts, int n_utts,
+                      int max_tokens, int max_frames, int medfilt_width, float qk_scale, float *d_ws, unsigned flags,
+                      int sm_count, cudaStream_t stream) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        WCA_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) {
+            set_error("capture_tc: the driver does not export cuTensorMapEncodeTiled");
+            return WCA_ERR_CUDA;
+        }
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    tc::TensorMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    for (int l = 0; l < n_layers; ++l) {
+        int rc = encode_map(encode, &maps.q[l], h_q_layers[l], q_rows, (int64_t)n_heads * kHeadDim, ld_q);
+        if (rc) return rc;
+        rc = encode_map(encode, &maps.k[l], h_k_layers[l], k_rows, (int64_t)n_heads * kHeadDim, ld_k);
+        if (rc) return rc;
     }
     int csize = 1;
     while (csize < 8 && ((((max_frames + csize - 1) / csize) + 15) & ~15) > tc::kMaxOwn) csize *= 2;
@@ -674,8 +728,6 @@ int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_la
     tc::KernelArgs a;
     a.utts = d_utts;
     a.ws = d_ws;
-    a.ld_q = ld_q;
-    a.ld_k = ld_k;
     a.n_heads = n_heads;
     a.lh_count = lh_count;
     a.tok_blocks = tok_blocks;
@@ -705,7 +757,7 @@ int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_la
     do {                                                                                                        \
         WCA_CUDA(cudaFuncSetAttribute(tc::capture_tc_kernel<Wv>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                       tc::kSmemBytes));                                                         \
-        WCA_CUDA(cudaLaunchKernelEx(&cfg, tc::capture_tc_kernel<Wv>, p, a));                                    \
+        WCA_CUDA(cudaLaunchKernelEx(&cfg, tc::capture_tc_kernel<Wv>, maps, a));                                 \
     } while (0)
     switch (width) {
         case 1: WCA_GO(1); break;
