@@ -71,8 +71,19 @@ constexpr int kOffKLo = kOffKHi + 2 * kKSplitBytes;
 constexpr int kOffTile = kOffKLo + 2 * kKSplitBytes;            // 8 epilogue warps x 32 x 17 floats
 constexpr int kOffStat = kOffTile + 8 * 32 * kTilePitch * 4;    // smax[2][128], ssum[2][128]
 constexpr int kOffBar = kOffStat + 4 * kRows * 4;
-enum Bar { kStageFull = 0, kStageEmpty = 3, kAReady = 6, kAFree = 7, kBReady = 8, kBFree = 10, kAccFull = 12,
-           kAccEmpty = 14, kXMax = 16, kXSum = 18, kNumBars = 20 };
+enum Bar {
+    kStageFull = 0,
+    kStageEmpty = kStageFull + kStages,
+    kAReady = kStageEmpty + kStages,
+    kAFree = kAReady + 1,
+    kBReady = kAFree + 1,
+    kBFree = kBReady + 2,
+    kAccFull = kBFree + 2,
+    kAccEmpty = kAccFull + 2,
+    kXMax = kAccEmpty + 2,
+    kXSum = kXMax + 2,
+    kNumBars = kXSum + 2
+};
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
