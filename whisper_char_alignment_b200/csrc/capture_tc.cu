@@ -258,6 +258,19 @@ __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
 __device__ __forceinline__ void tmem_st1(uint32_t taddr, float v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "f"(v) : "memory");
 }
+// Exactly one lane of a converged warp gets true; keeps the surrounding code warp-uniform so
+// descriptors live in uniform registers instead of being broadcast lane by lane.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -570,47 +583,49 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            uint32_t n_tile = 0, n_chunk = 0, acc_use[2] = {0, 0}, it = 0;
-            const uint32_t a_hi = smem_u32(smem + kOffQHi), a_lo = smem_u32(smem + kOffQLo);
-            for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
-                const Geo g = decode_tile<W>(a, tile, crank, csize);
-                if (!g.live) continue;
-                const uint32_t buf = it & 1u;
-                ++it;
-                if (g.n_own == 0) continue;
-                mbar_wait(bar(kAccEmpty + buf), (acc_use[buf] & 1u) ^ 1u);  // epilogue drained this accumulator
-                ++acc_use[buf];
-                mbar_wait(bar(kAReady), n_tile & 1u);
-                ++n_tile;
-                for (int j = 0; j < g.n_chunks; ++j) {
-                    const uint32_t kb = n_chunk & 1u;
-                    mbar_wait(bar(kBReady + kb), (n_chunk >> 1) & 1u);
-                    ++n_chunk;
-                    tc_fence_after();
-                    const int n_cols = (min(kChunk, g.n_mma - j * kChunk) + 15) & ~15;  // UMMA N: multiple of 16
-                    const uint32_t idesc = instr_desc_tf32(kRows, n_cols);
-                    const uint32_t d = tmem_base + buf * kAccCols + (uint32_t)(g.mcol0 + j * kChunk);
-                    const uint32_t b_hi = smem_u32(smem + kOffKHi) + kb * kKSplitBytes;
-                    const uint32_t b_lo = smem_u32(smem + kOffKLo) + kb * kKSplitBytes;
+        // ================= MMA issuer: warp-uniform control flow, one elected lane issues =================
+        uint32_t n_tile = 0, n_chunk = 0, acc_use[2] = {0, 0}, it = 0;
+        const uint32_t a_hi = smem_u32(smem + kOffQHi), a_lo = smem_u32(smem + kOffQLo);
+        for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
+            const Geo g = decode_tile<W>(a, tile, crank, csize);
+            if (!g.live) continue;
+            const uint32_t buf = it & 1u;
+            ++it;
+            if (g.n_own == 0) continue;
+            mbar_wait(bar(kAccEmpty + buf), (acc_use[buf] & 1u) ^ 1u);  // epilogue drained this accumulator
+            ++acc_use[buf];
+            mbar_wait(bar(kAReady), n_tile & 1u);
+            ++n_tile;
+            for (int j = 0; j < g.n_chunks; ++j) {
+                const uint32_t kb = n_chunk & 1u;
+                mbar_wait(bar(kBReady + kb), (n_chunk >> 1) & 1u);
+                ++n_chunk;
+                tc_fence_after();
+                const int n_cols = (min(kChunk, g.n_mma - j * kChunk) + 15) & ~15;  // UMMA N: multiple of 16
+                const uint32_t idesc = instr_desc_tf32(kRows, n_cols);
+                const uint32_t d = tmem_base + buf * kAccCols + (uint32_t)(g.mcol0 + j * kChunk);
+                const uint32_t b_hi = smem_u32(smem + kOffKHi) + kb * kKSplitBytes;
+                const uint32_t b_lo = smem_u32(smem + kOffKLo) + kb * kKSplitBytes;
+                if (elect_one()) {
                     // small terms first: lo*hi, hi*lo, then hi*hi
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t pa = pass == 0 ? a_lo : a_hi;
-                        const uint32_t pb = pass == 1 ? b_lo : b_hi;
+                        const uint64_t da = smem_desc(pass == 0 ? a_lo : a_hi, kLboQ, kSbo);
+                        const uint64_t db = smem_desc(pass == 1 ? b_lo : b_hi, kLboK, kSbo);
 #pragma unroll
-                        for (int ks = 0; ks < kHeadDim / 8; ++ks)  // K = 8 tf32 (two 16-byte k-chunks) per instruction
-                            umma_tf32(d, smem_desc(pa + ks * 2 * kLboQ, kLboQ, kSbo),
-                                      smem_desc(pb + ks * 2 * kLboK, kLboK, kSbo), idesc, (pass | ks) != 0);
+                        for (int ks = 0; ks < kHeadDim / 8; ++ks)  // K = 8 tf32 = two 16-byte k-chunks per instruction
+                            umma_tf32(d, da + (uint64_t)(ks * ((2 * kLboQ) >> 4)), db + (uint64_t)(ks * ((2 * kLboK) >> 4)),
+                                      idesc, (pass | ks) != 0);
                     }
                     umma_commit(bar(kBFree + kb));
+                    if (j == g.n_chunks - 1) {
+                        umma_commit(bar(kAFree));
+                        umma_commit(bar(kAccFull + buf));
+                    }
                 }
-                umma_commit(bar(kAFree));
-                umma_commit(bar(kAccFull + buf));
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else if (warp >= 4 && warp < 8) {
         // ================= operand splitters =================
         const int t = tid - 4 * 32;
