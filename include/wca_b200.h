@@ -88,11 +88,16 @@ WCA_API int wca_device_info(int *sm_count, int *compute_capability);
  * Output: d_ws + ws_off, layout (L, H, T, F) fp32, exactly what get_attentions returns. */
 #define WCA_CAPTURE_RAW_LOGITS 1u
 #define WCA_CAPTURE_FORCE_SIMT 2u /* use the CUDA-core kernel instead of tcgen05 (test cross-check) */
+#define WCA_CAPTURE_TRACE 4u      /* debug: CTA 0 records a clock64 timeline, see wca_debug_capture_trace */
 WCA_API int wca_capture_attention(const float *const *h_q_layers, const float *const *h_k_layers, int n_layers,
                           int n_heads_per_layer, int head_dim, int64_t ld_q, int64_t ld_k,
                           int64_t q_rows, int64_t k_rows, const wca_utt_t *d_utts, int n_utts, int max_tokens, int max_frames,
                           int medfilt_width, float qk_scale, float *d_ws, unsigned flags,
                           wca_stream_t stream);
+
+/* Debug only: copies the timeline recorded by the last WCA_CAPTURE_TRACE launch (synchronises
+ * the device).  Returns the number of int64 entries written (tiles x events) or a status < 0. */
+WCA_API int wca_debug_capture_trace(long long *h_out, int capacity);
 
 /* (2) Median filter -> *qk_scale -> softmax over already materialised logits.
  * Replaces timing.py:64-66 (`weights[..., :max_frames]`, whisper.timing.median_filter,

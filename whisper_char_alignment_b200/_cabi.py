@@ -18,11 +18,12 @@ LIB_PATH = os.path.join(_PKG_DIR, "libwca_b200.so")
 
 WCA_CAPTURE_RAW_LOGITS = 1
 WCA_CAPTURE_FORCE_SIMT = 2
+WCA_CAPTURE_TRACE = 4
 WCA_MAX_LAYERS = 64
 ABI_VERSION = 2
 
 EXPORTS = (
-    "wca_abi_version", "wca_last_error", "wca_launch_count", "wca_device_info", "wca_capture_attention", "wca_medfilt_softmax",
+    "wca_abi_version", "wca_last_error", "wca_launch_count", "wca_device_info", "wca_capture_attention", "wca_debug_capture_trace", "wca_medfilt_softmax",
     "wca_head_scores", "wca_topk_heads", "wca_aggregate_heads", "wca_dtw_workspace_bytes", "wca_dtw_align",
 )
 
@@ -161,6 +162,15 @@ def _dev_ptr(t: torch.Tensor | None, dtype=None, name="tensor") -> int | None:
     if not t.is_contiguous():
         raise WcaError(f"{name} must be contiguous")
     return t.data_ptr()
+
+
+def capture_trace():
+    """(tiles, events) int64 clock64 stamps of the last WCA_CAPTURE_TRACE launch (debug)."""
+    buf = (ctypes.c_longlong * 4096)()
+    n = load().wca_debug_capture_trace(buf, 4096)
+    if n < 0:
+        _check(n, "wca_debug_capture_trace")
+    return np.frombuffer(buf, dtype=np.int64, count=n).copy()
 
 
 def device_info():

@@ -43,6 +43,7 @@ int launch_capture_logits_simt(const float *const *, const float *const *, int, 
 int launch_capture_tc(const float *const *, const float *const *, int, int, int64_t, int64_t, int64_t, int64_t,
                       const wca_utt_t *, int, int, int, int, float, float *, unsigned, int, cudaStream_t);
 bool capture_tc_supported(int max_tokens, int max_frames, int medfilt_width);
+int read_capture_trace(long long *, int);
 int launch_medfilt_softmax_rows(const float *, int64_t, int64_t, int, int, float, float *, int, cudaStream_t);
 int launch_medfilt_softmax_batched(float *, const wca_utt_t *, int, int, int, int, int, float, int, cudaStream_t);
 int launch_head_scores(const float *, const wca_utt_t *, int, int, float, float, float, float *, cudaStream_t);
@@ -117,6 +118,11 @@ int wca_capture_attention(const float *const *h_q_layers, const float *const *h_
     if (rc || raw) return rc;
     return launch_medfilt_softmax_batched(d_ws, d_utts, n_utts, n_layers * n_heads_per_layer, max_tokens, max_frames,
                                           medfilt_width, qk_scale, sms, st);
+}
+
+int wca_debug_capture_trace(long long *h_out, int capacity) {
+    WCA_CHECK_ARG(h_out && capacity > 0, "wca_debug_capture_trace: bad buffer");
+    return read_capture_trace(h_out, capacity);
 }
 
 int wca_medfilt_softmax(const float *d_in, int64_t n_rows, int64_t ld_in, int n_frames, int medfilt_width,

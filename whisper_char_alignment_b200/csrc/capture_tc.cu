@@ -277,6 +277,17 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// ------------------------------------------------------------------ debug trace (WCA_CAPTURE_TRACE)
+// CTA 0 stamps clock64() at the hand-over points of every role for its first kTraceTiles
+// tiles; tools/trace_capture.py turns the table into a per-role timeline.
+constexpr int kTraceTiles = 40;
+enum Ev { kEvProdQ = 0, kEvProdK0, kEvProdKLast, kEvSplAFree, kEvSplQDone, kEvSplK0Done, kEvSplKLast, kEvMmaAccEmpty,
+          kEvMmaAReady, kEvMmaB0, kEvMmaIssued, kEvEpiAccFull, kEvEpiA, kEvEpiXMax, kEvEpiB, kEvEpiXSum, kEvEpiC, kNumEv };
+__device__ long long g_trace[kTraceTiles][kNumEv];
+__device__ __forceinline__ void stamp(bool on, uint32_t tile_seq, int ev) {
+    if (on && tile_seq < (uint32_t)kTraceTiles) g_trace[tile_seq][ev] = clock64();
+}
+
 // ------------------------------------------------------------------ tile geometry
 struct TensorMaps {
     CUtensorMap q[WCA_MAX_LAYERS];  // (rows, H*64) fp32 matrices, box 64 rows x 32 floats, 128B swizzle
@@ -289,6 +300,7 @@ struct KernelArgs {
     int n_heads, lh_count, tok_blocks, n_tiles;
     float s, qk_scale;
     int raw_logits;
+    int trace;
 };
 
 struct Geo {
@@ -396,7 +408,8 @@ __device__ __forceinline__ void median_block(const float (&prev)[16], const floa
 // The three sweeps of one tile by one epilogue warpgroup (thread <-> token row).
 template <int W>
 __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a, unsigned char *smem, uint32_t acc,
-                                              int grp, int ewarp, int lane, uint32_t csize, uint32_t x_parity) {
+                                              int grp, int ewarp, int lane, uint32_t csize, uint32_t x_parity,
+                                              bool tr, uint32_t seq) {
     const int row = ewarp * 32 + lane;
     const bool row_ok = row < g.rows_valid;
     const bool sweep = (ewarp * 32 < g.rows_valid) && g.n_own > 0;  // warp-uniform
@@ -451,6 +464,7 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
             }
             tmem_wait_st();
         }
+        stamp(tr, seq, kEvEpiA);
         // exchange the row maxima across the cluster (every CTA takes part, even with no own frames)
         smax[row] = row_ok ? row_max : -INFINITY;
         named_bar_sync(1 + grp, kEpiThreads);
@@ -459,6 +473,7 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
         mbar_wait_cluster(bar_xmax, x_parity);
         float gmax = -INFINITY;
         for (uint32_t r = 0; r < csize; ++r) gmax = fmaxf(gmax, ld_dsmem_f32(&smax[row], r));
+        stamp(tr, seq, kEvEpiXMax);
 
         float row_sum = 0.f;
         if (sweep) {
@@ -482,6 +497,7 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
             }
             tmem_wait_st();
         }
+        stamp(tr, seq, kEvEpiB);
         ssum[row] = row_ok ? row_sum : 0.f;
         named_bar_sync(1 + grp, kEpiThreads);
         if (row == 0)
@@ -490,6 +506,7 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
         float gsum = 0.f;
         for (uint32_t r = 0; r < csize; ++r) gsum += ld_dsmem_f32(&ssum[row], r);
         inv_sum = 1.f / gsum;
+        stamp(tr, seq, kEvEpiXSum);
     }
 
     // sweep C: normalise, transpose 32x16 blocks through shared memory, coalesced row stores
@@ -519,6 +536,7 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
             for (int i = 0; i < 16; ++i) v[i] = ahead[i];
         }
     }
+    stamp(tr, seq, kEvEpiC);
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -563,7 +581,8 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
 
     if (warp == 0) {
         // ================= TMA producer =================
-        uint32_t n_item = 0;
+        uint32_t n_item = 0, seq = 0;
+        const bool tr = a.trace && blockIdx.x == 0 && lane == 0;
         const uint32_t stage0 = smem_u32(smem + kOffStage);
         for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
             const Geo g = decode_tile<W>(a, tile, crank, csize);
@@ -574,17 +593,21 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
                 producer_item(stage0 + s * kStageBytes, bar(kStageFull + s), bar(kStageEmpty + s), n_item,
                               &maps.q[g.layer], g.col0, g.qrow0 + h * kStageRows, lane);
                 ++n_item;
+                stamp(tr, seq, kEvProdQ);
             }
             for (int j = 0; j < g.n_chunks; ++j) {
                 const uint32_t s = n_item % kStages;
                 producer_item(stage0 + s * kStageBytes, bar(kStageFull + s), bar(kStageEmpty + s), n_item,
                               &maps.k[g.layer], g.col0, g.krow0 + g.m0 + j * kChunk, lane);
                 ++n_item;
+                stamp(tr, seq, j == 0 ? kEvProdK0 : kEvProdKLast);
             }
+            ++seq;
         }
     } else if (warp == 1) {
         // ================= MMA issuer: warp-uniform control flow, one elected lane issues =================
         uint32_t n_tile = 0, n_chunk = 0, acc_use[2] = {0, 0}, it = 0;
+        const bool tr = a.trace && blockIdx.x == 0 && lane == 0;
         const uint32_t a_hi = smem_u32(smem + kOffQHi), a_lo = smem_u32(smem + kOffQLo);
         for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
             const Geo g = decode_tile<W>(a, tile, crank, csize);
@@ -594,12 +617,15 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
             if (g.n_own == 0) continue;
             mbar_wait(bar(kAccEmpty + buf), (acc_use[buf] & 1u) ^ 1u);  // epilogue drained this accumulator
             ++acc_use[buf];
+            stamp(tr, n_tile, kEvMmaAccEmpty);
             mbar_wait(bar(kAReady), n_tile & 1u);
+            stamp(tr, n_tile, kEvMmaAReady);
             ++n_tile;
             for (int j = 0; j < g.n_chunks; ++j) {
                 const uint32_t kb = n_chunk & 1u;
                 mbar_wait(bar(kBReady + kb), (n_chunk >> 1) & 1u);
                 ++n_chunk;
+                if (j == 0) stamp(tr, n_tile - 1, kEvMmaB0);
                 tc_fence_after();
                 const int n_cols = (min(kChunk, g.n_mma - j * kChunk) + 15) & ~15;  // UMMA N: multiple of 16
                 const uint32_t idesc = instr_desc_tf32(kRows, n_cols);
@@ -625,15 +651,18 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
                 }
                 __syncwarp();
             }
+            stamp(tr, n_tile - 1, kEvMmaIssued);
         }
     } else if (warp >= 4 && warp < 8) {
         // ================= operand splitters =================
         const int t = tid - 4 * 32;
         uint32_t n_item = 0, n_tile = 0, n_chunk = 0;
+        const bool tr = a.trace && blockIdx.x == 0 && t == 0;
         for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
             const Geo g = decode_tile<W>(a, tile, crank, csize);
             if (!g.live || g.n_own == 0) continue;
             mbar_wait(bar(kAFree), (n_tile & 1u) ^ 1u);  // MMAs of the previous tile no longer read Q
+            stamp(tr, n_tile, kEvSplAFree);
             ++n_tile;
             for (int h = 0; h < 2; ++h) {
                 if (g.rows_valid - h * kStageRows <= 0) continue;
@@ -645,6 +674,7 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
                 ++n_item;
             }
             mbar_arrive(bar(kAReady));
+            stamp(tr, n_tile - 1, kEvSplQDone);
             for (int j = 0; j < g.n_chunks; ++j) {
                 const uint32_t s = n_item % kStages, kb = n_chunk & 1u;
                 mbar_wait(bar(kBFree + kb), ((n_chunk >> 1) & 1u) ^ 1u);  // MMA released this K buffer
@@ -653,6 +683,7 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
                             smem + kOffKLo + kb * kKSplitBytes, kLboK, 0, a.s, t);
                 mbar_arrive(bar(kStageEmpty + s));
                 mbar_arrive(bar(kBReady + kb));
+                stamp(tr, n_tile - 1, j == 0 ? kEvSplK0Done : kEvSplKLast);
                 ++n_item;
                 ++n_chunk;
             }
@@ -661,17 +692,20 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
         // ================= epilogue warpgroups (A: even tiles, B: odd tiles) =================
         const int grp = (warp - 8) >> 2, ewarp = warp & 3;
         uint32_t it = 0, acc_use = 0, n_x = 0;
+        const bool tr = a.trace && blockIdx.x == 0 && ewarp == 0 && lane == 0;
         for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
             const Geo g = decode_tile<W>(a, tile, crank, csize);
             if (!g.live) continue;
             const bool mine = (it & 1u) == (uint32_t)grp;
+            const uint32_t seq = it;
             ++it;
             if (!mine) continue;
             if (g.n_own > 0) {
                 mbar_wait(bar(kAccFull + grp), acc_use & 1u);
                 tc_fence_after();
             }
-            epilogue_tile<W>(g, a, smem, tmem_base + (uint32_t)grp * kAccCols, grp, ewarp, lane, csize, n_x & 1u);
+            stamp(tr, seq, kEvEpiAccFull);
+            epilogue_tile<W>(g, a, smem, tmem_base + (uint32_t)grp * kAccCols, grp, ewarp, lane, csize, n_x & 1u, tr, seq);
             ++n_x;
             if (g.n_own > 0) {
                 tc_fence_before();
@@ -692,6 +726,16 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
 }
 
 }  // namespace tc
+
+int read_capture_trace(long long *h_out, int capacity) {
+    const int n = tc::kTraceTiles * tc::kNumEv;
+    if (capacity < n) {
+        set_error("wca_debug_capture_trace: capacity %d < %d", capacity, n);
+        return WCA_ERR_INVALID;
+    }
+    WCA_CUDA(cudaMemcpyFromSymbol(h_out, tc::g_trace, sizeof(long long) * n));
+    return n;
+}
 
 bool capture_tc_supported(int max_tokens, int max_frames, int medfilt_width) {
     (void)max_tokens;
@@ -761,6 +805,7 @@ int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_la
     a.s = (float)0.35355339059327373;  // 64 ** -0.25 as the reference's fp32 scalar
     a.qk_scale = qk_scale;
     a.raw_logits = (flags & WCA_CAPTURE_RAW_LOGITS) ? 1 : 0;
+    a.trace = (flags & WCA_CAPTURE_TRACE) ? 1 : 0;
     const int width = a.raw_logits ? 1 : medfilt_width;
 
     long long clusters = sm_count / csize;  // one persistent CTA per SM
