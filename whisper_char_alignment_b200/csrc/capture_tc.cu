@@ -415,6 +415,7 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
     const bool sweep = (ewarp * 32 < g.rows_valid) && g.n_own > 0;  // warp-uniform
     const uint32_t trow = acc + ((uint32_t)(ewarp * 32) << 16) + kOwnCol0;  // own frame 0 of this lane quarter
     const int n_blocks = (g.n_own + 15) >> 4;
+    const int tail = g.n_own - 16 * (n_blocks - 1);  // valid columns of the last block (1..16)
     float *smax = reinterpret_cast<float *>(smem + kOffStat) + grp * kRows;
     float *ssum = reinterpret_cast<float *>(smem + kOffStat) + (2 + grp) * kRows;
     const uint32_t bar_xmax = smem_u32(smem + kOffBar) + 8u * (kXMax + grp);
@@ -440,6 +441,7 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
             tmem_ld_wait(prev);
             tmem_ld_wait(cur);
             tmem_ld_wait(next);
+#pragma unroll(W <= 3 ? 4 : 1)  // 4 = rotation period of prev/cur/next/ahead: the copies vanish
             for (int b = 0; b < n_blocks; ++b) {
                 if (b + 2 <= n_blocks) tmem_ld16_issue(trow + (uint32_t)(16 * (b + 2)), ahead);  // stays inside the accumulator
                 if (g.half > 0) {
@@ -449,9 +451,14 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
                     for (int i = 0; i < 16; ++i) med[i] = cur[i];
                 }
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    med[i] *= a.qk_scale;
-                    if (16 * b + i < g.n_own) row_max = fmaxf(row_max, med[i]);
+                for (int i = 0; i < 16; ++i) med[i] *= a.qk_scale;
+                if (b + 1 < n_blocks) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) row_max = fmaxf(row_max, med[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (i < tail) row_max = fmaxf(row_max, med[i]);
                 }
                 tmem_st16(trow + (uint32_t)(16 * b), med);
                 tmem_ld_wait(ahead);
@@ -465,14 +472,17 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
             tmem_wait_st();
         }
         stamp(tr, seq, kEvEpiA);
-        // exchange the row maxima across the cluster (every CTA takes part, even with no own frames)
-        smax[row] = row_ok ? row_max : -INFINITY;
-        named_bar_sync(1 + grp, kEpiThreads);
-        if (row == 0)
-            for (uint32_t r = 0; r < csize; ++r) mbar_arrive_remote(bar_xmax, r);
-        mbar_wait_cluster(bar_xmax, x_parity);
-        float gmax = -INFINITY;
-        for (uint32_t r = 0; r < csize; ++r) gmax = fmaxf(gmax, ld_dsmem_f32(&smax[row], r));
+        float gmax = row_max;
+        if (csize > 1) {
+            // exchange the row maxima across the cluster (every CTA takes part, even with no own frames)
+            smax[row] = row_ok ? row_max : -INFINITY;
+            named_bar_sync(1 + grp, kEpiThreads);
+            if (row == 0)
+                for (uint32_t r = 0; r < csize; ++r) mbar_arrive_remote(bar_xmax, r);
+            mbar_wait_cluster(bar_xmax, x_parity);
+            gmax = -INFINITY;
+            for (uint32_t r = 0; r < csize; ++r) gmax = fmaxf(gmax, ld_dsmem_f32(&smax[row], r));
+        }
         stamp(tr, seq, kEvEpiXMax);
 
         float row_sum = 0.f;
@@ -483,12 +493,18 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
             float v[16], ahead[16];
             tmem_ld16_issue(trow, v);
             tmem_ld_wait(v);
+#pragma unroll 2
             for (int b = 0; b < n_blocks; ++b) {
                 tmem_ld16_issue(trow + (uint32_t)(16 * (b + 1)), ahead);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    v[i] = ex2_approx(fmaf(v[i], kLog2e, -shift));
-                    if (16 * b + i < g.n_own) row_sum += v[i];
+                for (int i = 0; i < 16; ++i) v[i] = ex2_approx(fmaf(v[i], kLog2e, -shift));
+                if (b + 1 < n_blocks) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) row_sum += v[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (i < tail) row_sum += v[i];
                 }
                 tmem_st16(trow + (uint32_t)(16 * b), v);
                 tmem_ld_wait(ahead);
@@ -498,23 +514,31 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
             tmem_wait_st();
         }
         stamp(tr, seq, kEvEpiB);
-        ssum[row] = row_ok ? row_sum : 0.f;
-        named_bar_sync(1 + grp, kEpiThreads);
-        if (row == 0)
-            for (uint32_t r = 0; r < csize; ++r) mbar_arrive_remote(bar_xsum, r);
-        mbar_wait_cluster(bar_xsum, x_parity);
-        float gsum = 0.f;
-        for (uint32_t r = 0; r < csize; ++r) gsum += ld_dsmem_f32(&ssum[row], r);
+        float gsum = row_sum;
+        if (csize > 1) {
+            ssum[row] = row_ok ? row_sum : 0.f;
+            named_bar_sync(1 + grp, kEpiThreads);
+            if (row == 0)
+                for (uint32_t r = 0; r < csize; ++r) mbar_arrive_remote(bar_xsum, r);
+            mbar_wait_cluster(bar_xsum, x_parity);
+            gsum = 0.f;
+            for (uint32_t r = 0; r < csize; ++r) gsum += ld_dsmem_f32(&ssum[row], r);
+        }
         inv_sum = 1.f / gsum;
         stamp(tr, seq, kEvEpiXSum);
     }
 
-    // sweep C: normalise, transpose 32x16 blocks through shared memory, coalesced row stores
+    // sweep C: normalise, transpose 32x16 blocks through shared memory, coalesced row stores.
+    // Lane (c, rsel) stores column c of rows rsel, rsel+2, ...: two 64-byte row segments per
+    // instruction, the address advancing by two rows per step.
     if (sweep) {
         float *tile = reinterpret_cast<float *>(smem + kOffTile) + (grp * 4 + ewarp) * (32 * kTilePitch);
         const int rows_here = min(32, g.rows_valid - ewarp * 32);
-        const int c = lane & 15, rsel = lane >> 4;  // two rows of 16 columns per store instruction
-        float *orow = g.out + (int64_t)(ewarp * 32 + rsel) * g.F + g.f0 + c;
+        const int c = lane & 15, rsel = lane >> 4;
+        const int n_steps = (rows_here - rsel + 1) >> 1;  // rows rsel + 2k < rows_here
+        const int64_t step = 2 * (int64_t)g.F;
+        float *obase = g.out + (int64_t)(ewarp * 32 + rsel) * g.F + g.f0 + c;
+        const float *tsrc = tile + rsel * kTilePitch + c;
         float v[16], ahead[16];
         tmem_ld16_issue(trow, v);
         tmem_ld_wait(v);
@@ -523,13 +547,14 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
 #pragma unroll
             for (int i = 0; i < 16; ++i) tile[lane * kTilePitch + i] = v[i] * inv_sum;
             __syncwarp();
-            float o[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) o[k] = tile[(2 * k + rsel) * kTilePitch + c];
-            const bool col_ok = g.f0 + 16 * b + c < g.f1;
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-                if (col_ok && 2 * k + rsel < rows_here) st_stream(orow + (int64_t)(2 * k) * g.F + 16 * b, o[k]);
+            if (g.f0 + 16 * b + c < g.f1) {
+                float *p = obase + 16 * b;
+#pragma unroll 4
+                for (int k = 0; k < n_steps; ++k) {
+                    st_stream(p, tsrc[k * 2 * kTilePitch]);
+                    p += step;
+                }
+            }
             __syncwarp();
             tmem_ld_wait(ahead);
 #pragma unroll
