@@ -9,6 +9,7 @@ EV = ["ProdQ", "ProdK0", "ProdKLast", "SplAFree", "SplQDone", "SplK0Done", "SplK
 shape = sys.argv[1] if len(sys.argv) > 1 else "timit"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 width = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+dbg = int(sys.argv[4], 0) if len(sys.argv) > 4 else 0
 dev = torch.device("cuda:0")
 L, H, D, n_ctx = 24, 16, 64, 1500
 rng = np.random.default_rng(0)
@@ -29,7 +30,7 @@ d_utts = _cabi.upload_utts(recs, dev)
 ws = torch.empty(off, device=dev)
 for _ in range(2):
     _cabi.capture_attention(q, k, H, H * D, H * D, d_utts, B, t_max, int(Fs.max()), width, 1.0, ws, 0)
-_cabi.capture_attention(q, k, H, H * D, H * D, d_utts, B, t_max, int(Fs.max()), width, 1.0, ws, _cabi.WCA_CAPTURE_TRACE)
+_cabi.capture_attention(q, k, H, H * D, H * D, d_utts, B, t_max, int(Fs.max()), width, 1.0, ws, _cabi.WCA_CAPTURE_TRACE | dbg)
 torch.cuda.synchronize()
 tr = _cabi.capture_trace().reshape(-1, len(EV)).astype(np.float64)
 t0 = tr[tr > 0].min()

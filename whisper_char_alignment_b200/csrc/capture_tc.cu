@@ -301,6 +301,7 @@ struct KernelArgs {
     float s, qk_scale;
     int raw_logits;
     int trace;
+    unsigned dbg;  // experiment switches (bits 8..): never set by the product path
 };
 
 struct Geo {
@@ -310,6 +311,7 @@ struct Geo {
     int half;                // filter half-width actually applied (0: identity)
     int m0, mcol0, n_mma;    // first frame / accumulator column / frame count the MMA computes
     int n_chunks;
+    bool dup;                // <= 64 token rows and a single-CTA cluster: rows are mirrored into A rows 64..127
     int layer, col0;         // decoder layer and first float column of the head
     int qrow0, krow0;        // first Q row of the tile / first K row of the utterance
     float *out;              // row 0 of this tile, frame 0
@@ -342,6 +344,7 @@ __device__ __forceinline__ Geo decode_tile(const KernelArgs &a, int tile, uint32
     g.mcol0 = g.f0 > 0 ? 0 : kOwnCol0;  // frame f always sits at accumulator column f - f0 + 16
     g.n_mma = g.n_own > 0 ? min(g.f1 + kHalo, g.F) - g.m0 : 0;
     g.n_chunks = (g.n_mma + kChunk - 1) / kChunk;
+    g.dup = csize == 1 && g.rows_valid <= kStageRows;
     return g;
 }
 
@@ -360,7 +363,7 @@ __device__ __forceinline__ void producer_item(uint32_t stage, uint32_t bar_full,
 
 // 128 splitter threads: staging tile (64 rows) -> scaled hi / lo parts in UMMA no-swizzle layout.
 __device__ __forceinline__ void split_stage(const unsigned char *stage, unsigned char *hi, unsigned char *lo,
-                                            uint32_t lbo, int row_off, float s, int t) {
+                                            uint32_t lbo, int row_off, float s, int t, bool mirror = false) {
 #pragma unroll
     for (int it = 0; it < (kStageRows * 16) / kSplitThreads; ++it) {
         const int e = it * kSplitThreads + t;
@@ -379,6 +382,10 @@ __device__ __forceinline__ void split_stage(const unsigned char *stage, unsigned
         const uint32_t off = (uint32_t)ch * lbo + (uint32_t)(row + row_off) * 16u;
         *reinterpret_cast<float4 *>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<float4 *>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+        if (mirror) {  // second copy of the token rows in A rows 64..127 (see Geo::dup)
+            *reinterpret_cast<float4 *>(hi + off + kStageRows * 16u) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4 *>(lo + off + kStageRows * 16u) = make_float4(l[0], l[1], l[2], l[3]);
+        }
     }
     fence_proxy_async_smem();  // generic-proxy stores must be visible to the tensor core's async proxy
 }
@@ -410,11 +417,18 @@ template <int W>
 __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a, unsigned char *smem, uint32_t acc,
                                               int grp, int ewarp, int lane, uint32_t csize, uint32_t x_parity,
                                               bool tr, uint32_t seq) {
-    const int row = ewarp * 32 + lane;
+    // Mirrored tiles (Geo::dup): lane quarters 2 and 3 hold a copy of token rows 0..63, so warps
+    // 2/3 (other two schedulers) take the second half of the columns of the rows of warps 0/1.
+    const int lw = g.dup ? (ewarp & 1) : ewarp;  // logical 32-row group
+    const int row = lw * 32 + lane;
     const bool row_ok = row < g.rows_valid;
-    const bool sweep = (ewarp * 32 < g.rows_valid) && g.n_own > 0;  // warp-uniform
-    const uint32_t trow = acc + ((uint32_t)(ewarp * 32) << 16) + kOwnCol0;  // own frame 0 of this lane quarter
     const int n_blocks = (g.n_own + 15) >> 4;
+    const int split = g.dup ? (n_blocks + 1) >> 1 : n_blocks;
+    const int b_lo = (g.dup && ewarp >= 2) ? split : 0;
+    const int b_hi = (g.dup && ewarp >= 2) ? n_blocks : split;
+    const bool rows_live = (lw * 32 < g.rows_valid) && g.n_own > 0;  // warp-uniform
+    const bool sweep = rows_live && b_lo < b_hi;
+    const uint32_t trow = acc + ((uint32_t)(ewarp * 32) << 16) + kOwnCol0;  // own frame 0 of this lane quarter
     const int tail = g.n_own - 16 * (n_blocks - 1);  // valid columns of the last block (1..16)
     float *smax = reinterpret_cast<float *>(smem + kOffStat) + grp * kRows;
     float *ssum = reinterpret_cast<float *>(smem + kOffStat) + (2 + grp) * kRows;
@@ -424,8 +438,8 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
     float inv_sum = 1.f;
     if (!a.raw_logits) {
         float row_max = -INFINITY;
-        if (sweep) {
-            if (g.half > 0) {
+        if (rows_live && g.half > 0) {
+            {
                 // materialise the reflect padding in TMEM: frame -i <- frame i, frame F-1+i <- frame F-1-i
                 if (g.f0 == 0)
                     for (int i = 1; i <= g.half; ++i) tmem_st1(trow - (uint32_t)i, tmem_ld1(trow + (uint32_t)i));
@@ -433,16 +447,18 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
                     tmem_st1(trow + (uint32_t)(f - g.f0), tmem_ld1(trow + (uint32_t)(2 * (g.F - 1) - f - g.f0)));
                 tmem_wait_st();
             }
+        }
+        if (sweep) {
             // sweep A: median filter in place, * qk_scale, running max; the load of block b+2 is in flight
             float prev[16], cur[16], next[16], ahead[16], med[16];
-            tmem_ld16_issue(trow - 16u, prev);
-            tmem_ld16_issue(trow, cur);
-            tmem_ld16_issue(trow + 16u, next);
+            tmem_ld16_issue(trow + (uint32_t)(16 * (b_lo - 1) + 16) - 16u, prev);
+            tmem_ld16_issue(trow + (uint32_t)(16 * b_lo), cur);
+            tmem_ld16_issue(trow + (uint32_t)(16 * (b_lo + 1)), next);
             tmem_ld_wait(prev);
             tmem_ld_wait(cur);
             tmem_ld_wait(next);
 #pragma unroll(W <= 3 ? 4 : 1)  // 4 = rotation period of prev/cur/next/ahead: the copies vanish
-            for (int b = 0; b < n_blocks; ++b) {
+            for (int b = b_lo; b < b_hi; ++b) {
                 if (b + 2 <= n_blocks) tmem_ld16_issue(trow + (uint32_t)(16 * (b + 2)), ahead);  // stays inside the accumulator
                 if (g.half > 0) {
                     median_block<W>(prev, cur, next, med);
@@ -473,6 +489,11 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
         }
         stamp(tr, seq, kEvEpiA);
         float gmax = row_max;
+        if (g.dup) {  // combine the two column halves of a mirrored tile
+            smax[ewarp * 32 + lane] = row_max;
+            named_bar_sync(1 + grp, kEpiThreads);
+            gmax = fmaxf(row_max, smax[(ewarp ^ 2) * 32 + lane]);
+        }
         if (csize > 1) {
             // exchange the row maxima across the cluster (every CTA takes part, even with no own frames)
             smax[row] = row_ok ? row_max : -INFINITY;
@@ -491,10 +512,10 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
             const float kLog2e = 1.4426950408889634f;
             const float shift = gmax * kLog2e;
             float v[16], ahead[16];
-            tmem_ld16_issue(trow, v);
+            tmem_ld16_issue(trow + (uint32_t)(16 * b_lo), v);
             tmem_ld_wait(v);
 #pragma unroll 2
-            for (int b = 0; b < n_blocks; ++b) {
+            for (int b = b_lo; b < b_hi; ++b) {
                 tmem_ld16_issue(trow + (uint32_t)(16 * (b + 1)), ahead);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = ex2_approx(fmaf(v[i], kLog2e, -shift));
@@ -515,6 +536,11 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
         }
         stamp(tr, seq, kEvEpiB);
         float gsum = row_sum;
+        if (g.dup) {
+            ssum[ewarp * 32 + lane] = row_sum;
+            named_bar_sync(1 + grp, kEpiThreads);
+            gsum = row_sum + ssum[(ewarp ^ 2) * 32 + lane];
+        }
         if (csize > 1) {
             ssum[row] = row_ok ? row_sum : 0.f;
             named_bar_sync(1 + grp, kEpiThreads);
@@ -533,16 +559,16 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
     // instruction, the address advancing by two rows per step.
     if (sweep) {
         float *tile = reinterpret_cast<float *>(smem + kOffTile) + (grp * 4 + ewarp) * (32 * kTilePitch);
-        const int rows_here = min(32, g.rows_valid - ewarp * 32);
+        const int rows_here = min(32, g.rows_valid - lw * 32);
         const int c = lane & 15, rsel = lane >> 4;
         const int n_steps = (rows_here - rsel + 1) >> 1;  // rows rsel + 2k < rows_here
         const int64_t step = 2 * (int64_t)g.F;
-        float *obase = g.out + (int64_t)(ewarp * 32 + rsel) * g.F + g.f0 + c;
+        float *obase = g.out + (int64_t)(lw * 32 + rsel) * g.F + g.f0 + c;
         const float *tsrc = tile + rsel * kTilePitch + c;
         float v[16], ahead[16];
-        tmem_ld16_issue(trow, v);
+        tmem_ld16_issue(trow + (uint32_t)(16 * b_lo), v);
         tmem_ld_wait(v);
-        for (int b = 0; b < n_blocks; ++b) {
+        for (int b = b_lo; b < b_hi; ++b) {
             tmem_ld16_issue(trow + (uint32_t)(16 * (b + 1)), ahead);
 #pragma unroll
             for (int i = 0; i < 16; ++i) tile[lane * kTilePitch + i] = v[i] * inv_sum;
@@ -551,7 +577,9 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
                 float *p = obase + 16 * b;
 #pragma unroll 4
                 for (int k = 0; k < n_steps; ++k) {
-                    st_stream(p, tsrc[k * 2 * kTilePitch]);
+                    const float val = tsrc[k * 2 * kTilePitch];
+                    if (!(a.dbg & 0x100u)) st_stream(p, val);
+                    else if (val == 123.456f) st_stream(p, val);
                     p += step;
                 }
             }
@@ -694,7 +722,7 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
                 const uint32_t s = n_item % kStages;
                 mbar_wait(bar(kStageFull + s), (n_item / kStages) & 1u);
                 split_stage(smem + kOffStage + s * kStageBytes, smem + kOffQHi, smem + kOffQLo, kLboQ, h * kStageRows,
-                            a.s, t);
+                            a.s, t, g.dup);
                 mbar_arrive(bar(kStageEmpty + s));
                 ++n_item;
             }
@@ -831,6 +859,7 @@ int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_la
     a.qk_scale = qk_scale;
     a.raw_logits = (flags & WCA_CAPTURE_RAW_LOGITS) ? 1 : 0;
     a.trace = (flags & WCA_CAPTURE_TRACE) ? 1 : 0;
+    a.dbg = flags & 0xff00u;
     const int width = a.raw_logits ? 1 : medfilt_width;
 
     long long clusters = sm_count / csize;  // one persistent CTA per SM
