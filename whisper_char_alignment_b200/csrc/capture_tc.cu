@@ -348,6 +348,21 @@ __device__ __forceinline__ Geo decode_tile(const KernelArgs &a, int tile, uint32
     return g;
 }
 
+// Staging items of one tile, in ring order: K chunk 0, then the Q halves, then K chunks 1..
+// (K0 first so that it can be split while the previous tile's MMAs still read the Q buffers).
+struct Item {
+    bool is_q;
+    int index;  // Q half (0/1) or K chunk
+};
+__device__ __forceinline__ int tile_items(const Geo &g) { return g.n_chunks + (g.rows_valid > kStageRows ? 2 : 1); }
+__device__ __forceinline__ Item tile_item(const Geo &g, int i) {
+    const int n_q = g.rows_valid > kStageRows ? 2 : 1;
+    Item it;
+    it.is_q = i >= 1 && i <= n_q;
+    it.index = i == 0 ? 0 : (it.is_q ? i - 1 : i - n_q);
+    return it;
+}
+
 // ------------------------------------------------------------------ role bodies
 // One elected lane arms the stage barrier and issues the two column-half boxes of a 64-row tile.
 __device__ __forceinline__ void producer_item(uint32_t stage, uint32_t bar_full, uint32_t bar_empty, uint32_t n_item,
@@ -364,14 +379,21 @@ __device__ __forceinline__ void producer_item(uint32_t stage, uint32_t bar_full,
 // 128 splitter threads: staging tile (64 rows) -> scaled hi / lo parts in UMMA no-swizzle layout.
 __device__ __forceinline__ void split_stage(const unsigned char *stage, unsigned char *hi, unsigned char *lo,
                                             uint32_t lbo, int row_off, float s, int t, bool mirror = false) {
+    constexpr int kIters = (kStageRows * 16) / kSplitThreads;  // 8 float4 per thread
+    // e = it * 128 + t  ->  row = t & 63 (fixed per thread), 16-byte chunk ch = 2 * it + (t >> 6)
+    const int row = t & (kStageRows - 1);
+    const int ch0 = t >> 6;
+    float4 v[kIters];
 #pragma unroll
-    for (int it = 0; it < (kStageRows * 16) / kSplitThreads; ++it) {
-        const int e = it * kSplitThreads + t;
-        const int row = e & (kStageRows - 1), ch = e >> 6;
+    for (int it = 0; it < kIters; ++it) {  // all loads in flight before any arithmetic
+        const int ch = 2 * it + ch0;
         // 128-byte swizzle of the TMA box: 16-byte chunk c of row r sits at chunk position c ^ (r & 7)
-        const float4 v = *reinterpret_cast<const float4 *>(stage + (ch >> 3) * kBoxBytes + row * 128 +
-                                                           (((ch & 7) ^ (row & 7)) << 4));
-        const float x[4] = {v.x * s, v.y * s, v.z * s, v.w * s};
+        v[it] = *reinterpret_cast<const float4 *>(stage + (ch >> 3) * kBoxBytes + row * 128 + (((ch & 7) ^ (row & 7)) << 4));
+    }
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+        const int ch = 2 * it + ch0;
+        const float x[4] = {v[it].x * s, v[it].y * s, v[it].z * s, v[it].w * s};
         float h[4], l[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -573,13 +595,14 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
 #pragma unroll
             for (int i = 0; i < 16; ++i) tile[lane * kTilePitch + i] = v[i] * inv_sum;
             __syncwarp();
+            float o[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) o[k] = tsrc[k * 2 * kTilePitch];  // all reads in flight before the stores
             if (g.f0 + 16 * b + c < g.f1) {
                 float *p = obase + 16 * b;
-#pragma unroll 4
-                for (int k = 0; k < n_steps; ++k) {
-                    const float val = tsrc[k * 2 * kTilePitch];
-                    if (!(a.dbg & 0x100u)) st_stream(p, val);
-                    else if (val == 123.456f) st_stream(p, val);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if (k < n_steps) st_stream(p, o[k]);
                     p += step;
                 }
             }
@@ -640,20 +663,18 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
         for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
             const Geo g = decode_tile<W>(a, tile, crank, csize);
             if (!g.live || g.n_own == 0) continue;
-            for (int h = 0; h < 2; ++h) {  // Q in two 64-row halves
-                if (g.rows_valid - h * kStageRows <= 0) continue;
+            const int n_items = tile_items(g);
+            for (int i = 0; i < n_items; ++i) {
+                const Item item = tile_item(g, i);
                 const uint32_t s = n_item % kStages;
-                producer_item(stage0 + s * kStageBytes, bar(kStageFull + s), bar(kStageEmpty + s), n_item,
-                              &maps.q[g.layer], g.col0, g.qrow0 + h * kStageRows, lane);
+                if (item.is_q)
+                    producer_item(stage0 + s * kStageBytes, bar(kStageFull + s), bar(kStageEmpty + s), n_item,
+                                  &maps.q[g.layer], g.col0, g.qrow0 + item.index * kStageRows, lane);
+                else
+                    producer_item(stage0 + s * kStageBytes, bar(kStageFull + s), bar(kStageEmpty + s), n_item,
+                                  &maps.k[g.layer], g.col0, g.krow0 + g.m0 + item.index * kChunk, lane);
                 ++n_item;
-                stamp(tr, seq, kEvProdQ);
-            }
-            for (int j = 0; j < g.n_chunks; ++j) {
-                const uint32_t s = n_item % kStages;
-                producer_item(stage0 + s * kStageBytes, bar(kStageFull + s), bar(kStageEmpty + s), n_item,
-                              &maps.k[g.layer], g.col0, g.krow0 + g.m0 + j * kChunk, lane);
-                ++n_item;
-                stamp(tr, seq, j == 0 ? kEvProdK0 : kEvProdKLast);
+                stamp(tr, seq, item.is_q ? kEvProdQ : (item.index == 0 ? kEvProdK0 : kEvProdKLast));
             }
             ++seq;
         }
@@ -714,31 +735,37 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
         for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
             const Geo g = decode_tile<W>(a, tile, crank, csize);
             if (!g.live || g.n_own == 0) continue;
-            mbar_wait(bar(kAFree), (n_tile & 1u) ^ 1u);  // MMAs of the previous tile no longer read Q
-            stamp(tr, n_tile, kEvSplAFree);
-            ++n_tile;
-            for (int h = 0; h < 2; ++h) {
-                if (g.rows_valid - h * kStageRows <= 0) continue;
+            const int n_items = tile_items(g);
+            const int n_q = g.rows_valid > kStageRows ? 2 : 1;
+            for (int i = 0; i < n_items; ++i) {
+                const Item item = tile_item(g, i);
                 const uint32_t s = n_item % kStages;
-                mbar_wait(bar(kStageFull + s), (n_item / kStages) & 1u);
-                split_stage(smem + kOffStage + s * kStageBytes, smem + kOffQHi, smem + kOffQLo, kLboQ, h * kStageRows,
-                            a.s, t, g.dup);
-                mbar_arrive(bar(kStageEmpty + s));
+                if (item.is_q) {
+                    if (item.index == 0) {
+                        mbar_wait(bar(kAFree), (n_tile & 1u) ^ 1u);  // MMAs of the previous tile no longer read Q
+                        stamp(tr, n_tile, kEvSplAFree);
+                        ++n_tile;
+                    }
+                    mbar_wait(bar(kStageFull + s), (n_item / kStages) & 1u);
+                    split_stage(smem + kOffStage + s * kStageBytes, smem + kOffQHi, smem + kOffQLo, kLboQ,
+                                item.index * kStageRows, a.s, t, g.dup);
+                    mbar_arrive(bar(kStageEmpty + s));
+                    if (item.index == n_q - 1) {
+                        mbar_arrive(bar(kAReady));
+                        stamp(tr, n_tile - 1, kEvSplQDone);
+                    }
+                } else {
+                    const uint32_t kb = n_chunk & 1u;
+                    mbar_wait(bar(kBFree + kb), ((n_chunk >> 1) & 1u) ^ 1u);  // MMA released this K buffer
+                    mbar_wait(bar(kStageFull + s), (n_item / kStages) & 1u);
+                    split_stage(smem + kOffStage + s * kStageBytes, smem + kOffKHi + kb * kKSplitBytes,
+                                smem + kOffKLo + kb * kKSplitBytes, kLboK, 0, a.s, t);
+                    mbar_arrive(bar(kStageEmpty + s));
+                    mbar_arrive(bar(kBReady + kb));
+                    stamp(tr, n_tile - (item.index == 0 ? 0 : 1), item.index == 0 ? kEvSplK0Done : kEvSplKLast);
+                    ++n_chunk;
+                }
                 ++n_item;
-            }
-            mbar_arrive(bar(kAReady));
-            stamp(tr, n_tile - 1, kEvSplQDone);
-            for (int j = 0; j < g.n_chunks; ++j) {
-                const uint32_t s = n_item % kStages, kb = n_chunk & 1u;
-                mbar_wait(bar(kBFree + kb), ((n_chunk >> 1) & 1u) ^ 1u);  // MMA released this K buffer
-                mbar_wait(bar(kStageFull + s), (n_item / kStages) & 1u);
-                split_stage(smem + kOffStage + s * kStageBytes, smem + kOffKHi + kb * kKSplitBytes,
-                            smem + kOffKLo + kb * kKSplitBytes, kLboK, 0, a.s, t);
-                mbar_arrive(bar(kStageEmpty + s));
-                mbar_arrive(bar(kBReady + kb));
-                stamp(tr, n_tile - 1, j == 0 ? kEvSplK0Done : kEvSplKLast);
-                ++n_item;
-                ++n_chunk;
             }
         }
     } else if (warp >= 8) {
