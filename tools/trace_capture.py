@@ -5,7 +5,7 @@ import numpy as np, torch
 from whisper_char_alignment_b200 import _cabi
 
 EV = ["ProdQ", "ProdK0", "ProdKLast", "SplAFree", "SplQDone", "SplK0Done", "SplKLast", "MmaAccEmpty", "MmaAReady",
-      "MmaB0", "MmaIssued", "EpiAccFull", "EpiA", "EpiXMax", "EpiB", "EpiXSum", "EpiC"]
+      "MmaB0", "MmaIssued", "EpiAccFull", "EpiA", "EpiXMax", "EpiB", "EpiXSum", "EpiC", "SplFull", "SplLoaded", "SplStored", "SplFenced"]
 shape = sys.argv[1] if len(sys.argv) > 1 else "timit"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 width = int(sys.argv[3]) if len(sys.argv) > 3 else 3
@@ -56,3 +56,4 @@ print(" epilogue: xsum exchange                    :", d("EpiB", "EpiXSum"))
 print(" epilogue: sweep C                          :", d("EpiXSum", "EpiC"))
 print(" epilogue: total AccFull->C                 :", d("EpiAccFull", "EpiC"))
 print(" producer: Q issue -> KLast issue           :", d("ProdQ", "ProdKLast"))
+print(" Q split : AFree->Full | Full->Loaded | Loaded->Stored | Stored->Fenced | Fenced->QDone:", d("SplAFree","SplFull"), d("SplFull","SplLoaded"), d("SplLoaded","SplStored"), d("SplStored","SplFenced"), d("SplFenced","SplQDone"))

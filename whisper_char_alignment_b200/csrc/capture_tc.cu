@@ -282,7 +282,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // tiles; tools/trace_capture.py turns the table into a per-role timeline.
 constexpr int kTraceTiles = 40;
 enum Ev { kEvProdQ = 0, kEvProdK0, kEvProdKLast, kEvSplAFree, kEvSplQDone, kEvSplK0Done, kEvSplKLast, kEvMmaAccEmpty,
-          kEvMmaAReady, kEvMmaB0, kEvMmaIssued, kEvEpiAccFull, kEvEpiA, kEvEpiXMax, kEvEpiB, kEvEpiXSum, kEvEpiC, kNumEv };
+          kEvMmaAReady, kEvMmaB0, kEvMmaIssued, kEvEpiAccFull, kEvEpiA, kEvEpiXMax, kEvEpiB, kEvEpiXSum, kEvEpiC,
+          kEvSplFull, kEvSplLoaded, kEvSplStored, kEvSplFenced, kNumEv };
 __device__ long long g_trace[kTraceTiles][kNumEv];
 __device__ __forceinline__ void stamp(bool on, uint32_t tile_seq, int ev) {
     if (on && tile_seq < (uint32_t)kTraceTiles) g_trace[tile_seq][ev] = clock64();
@@ -378,7 +379,8 @@ __device__ __forceinline__ void producer_item(uint32_t stage, uint32_t bar_full,
 
 // 128 splitter threads: staging tile (64 rows) -> scaled hi / lo parts in UMMA no-swizzle layout.
 __device__ __forceinline__ void split_stage(const unsigned char *stage, unsigned char *hi, unsigned char *lo,
-                                            uint32_t lbo, int row_off, float s, int t, bool mirror = false) {
+                                            uint32_t lbo, int row_off, float s, int t, bool mirror = false,
+                                            bool tr = false, uint32_t seq = 0) {
     constexpr int kIters = (kStageRows * 16) / kSplitThreads;  // 8 float4 per thread
     // e = it * 128 + t  ->  row = t & 63 (fixed per thread), 16-byte chunk ch = 2 * it + (t >> 6)
     const int row = t & (kStageRows - 1);
@@ -390,6 +392,7 @@ __device__ __forceinline__ void split_stage(const unsigned char *stage, unsigned
         // 128-byte swizzle of the TMA box: 16-byte chunk c of row r sits at chunk position c ^ (r & 7)
         v[it] = *reinterpret_cast<const float4 *>(stage + (ch >> 3) * kBoxBytes + row * 128 + (((ch & 7) ^ (row & 7)) << 4));
     }
+    if (tr && v[0].x != 1e30f) stamp(tr, seq, kEvSplLoaded);
 #pragma unroll
     for (int it = 0; it < kIters; ++it) {
         const int ch = 2 * it + ch0;
@@ -409,7 +412,9 @@ __device__ __forceinline__ void split_stage(const unsigned char *stage, unsigned
             *reinterpret_cast<float4 *>(lo + off + kStageRows * 16u) = make_float4(l[0], l[1], l[2], l[3]);
         }
     }
+    stamp(tr, seq, kEvSplStored);
     fence_proxy_async_smem();  // generic-proxy stores must be visible to the tensor core's async proxy
+    stamp(tr, seq, kEvSplFenced);
 }
 
 // Sliding median over a 16-column block with its neighbour blocks; every index is a compile
@@ -747,8 +752,9 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
                         ++n_tile;
                     }
                     mbar_wait(bar(kStageFull + s), (n_item / kStages) & 1u);
+                    stamp(tr, n_tile - 1, kEvSplFull);
                     split_stage(smem + kOffStage + s * kStageBytes, smem + kOffQHi, smem + kOffQLo, kLboQ,
-                                item.index * kStageRows, a.s, t, g.dup);
+                                item.index * kStageRows, a.s, t, g.dup, tr, n_tile - 1);
                     mbar_arrive(bar(kStageEmpty + s));
                     if (item.index == n_q - 1) {
                         mbar_arrive(bar(kAReady));

@@ -66,6 +66,17 @@ class _CrossAttentionTap:
         return False
 
 
+_FRAMES_PER_CTA = 224  # csrc/capture_tc.cu: kMaxOwn
+
+
+def _cluster_bucket(n_frames: int) -> int:
+    """Cluster size (1, 2, 4 or 8 CTAs along frames) the capture kernel needs for this utterance."""
+    size = 1
+    while size < 8 and -(-n_frames // size) > _FRAMES_PER_CTA:
+        size *= 2
+    return size
+
+
 def _as_f32_rows(t: torch.Tensor) -> torch.Tensor:
     t = t.detach()
     if t.dtype != torch.float32:
@@ -115,11 +126,20 @@ def get_attentions_batch(mels, tokens_list: Sequence[torch.Tensor], model, token
         recs[b]["q_row0"], recs[b]["k_row0"] = b * t_max, b * k_layers[0].shape[1]
         recs[b]["ws_off"] = off
         off += n_layers * n_heads * lens[b] * frames[b]
-    d_utts = _cabi.upload_utts(recs, device)
     ws = torch.empty(off, dtype=torch.float32, device=device)
     flags = (_cabi.WCA_CAPTURE_RAW_LOGITS if raw_logits else 0) | (_cabi.WCA_CAPTURE_FORCE_SIMT if force_simt else 0)
-    _cabi.capture_attention(q_layers, k_layers, n_heads, width, width, d_utts, B, t_max, max(frames),
-                            int(medfilt_width), float(qk_scale), ws, flags)
+    # One launch per frame-count bucket: the capture kernel spreads an utterance's frames over a
+    # cluster of 1/2/4/8 CTAs (224 frames each) and the cluster size is a launch parameter, so
+    # short utterances must not share a launch with 30 s ones.
+    buckets = {}
+    for b in range(B):
+        buckets.setdefault(_cluster_bucket(frames[b]), []).append(b)
+    for _, members in sorted(buckets.items()):
+        sub = recs[members]
+        d_utts = _cabi.upload_utts(sub, device)
+        _cabi.capture_attention(q_layers, k_layers, n_heads, width, width, d_utts, len(members),
+                                int(sub["n_tokens"].max()), int(sub["n_frames"].max()), int(medfilt_width),
+                                float(qk_scale), ws, flags)
     weights, logits = [], []
     for b in range(B):
         n = n_layers * n_heads * lens[b] * frames[b]
