@@ -33,6 +33,15 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+# stdout carries exactly ONE line (the JSON result); library banners (NCCL version, ...) go to stderr
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+
+
 METRIC = "utterances/sec (Whisper-medium char align)"
 UNIT = "utt/s"
 
@@ -131,6 +140,13 @@ def cpu_reference_run(args, n_utts, warm):
     use_shim()
     from whisper.model import ModelDimensions as ODims, Whisper as OWhisper
 
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every host core
+    try:
+        n_cpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n_cpu = os.cpu_count() or 1
+    torch.set_num_threads(max(n_cpu, 1))
+
     from whisper_char_alignment_b200 import synthetic, whisper_model
     from whisper_char_alignment_b200.tokenizer import get_tokenizer
 
@@ -173,7 +189,7 @@ def run_reference(args):
         "e2e": {"value": ups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -337,7 +353,7 @@ def main():
             "dtw_cells_per_s": cells / (dtw_ms / max(dtw_calls, 1) / 1000.0) if dtw_ms > 0 else None,
             "utterances_aligned": len(local_alignments),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -2,131 +2,130 @@
 // Replaces reference timing.py:102-113: the `.cpu()` round trip, upstream
 // whisper.timing.dtw_cpu/backtrace (numba, single core) and the numpy jump extraction.
 //
-// One CTA per problem, thread r owns text row r+1 of the (N+1) x (M+1) cost table and
-// walks it left to right; all rows advance together along anti-diagonals (step s = i + j),
-// so each step needs only the neighbour's previous value, exchanged through a
-// double-buffered shared-memory line.  The 2-bit trace stays in shared memory (166 KB for
-// the largest legal Whisper problem, 445 x 1500), the backtrace runs on the device, and
-// only N jump frames / W word times ever leave the SM.
+// One WARP per problem.  Lane l owns a strip of R consecutive text rows (R = ceil(N/32),
+// compile-time 1..32) and walks it left to right, one column per step, one step behind lane
+// l-1: the anti-diagonal wavefront of the recurrence at strip granularity.  The only
+// exchange per step is one __shfl_up (the bottom row of the strip above), there is no block
+// barrier, and a 128-thread CTA runs four independent problems, so a batch of small
+// problems (BASELINE config 2: 41 x 150; config 5: 384 heads per utterance) fills the SMs
+// with independent dependency chains.  The trace is 2 bits per cell, packed per (column,
+// lane) word and kept in shared memory (global workspace only when a problem does not fit);
+// lane 0 backtraces on the device and only N jump frames / W word times leave the SM.
 //
 // Bit-exactness contract (must match dtw_cpu): fp32 round-to-nearest add, no FMA; the
 // diagonal wins only if strictly smaller than both others, then the text step only if
 // strictly smaller than both others, otherwise the time step -- so ties and NaN go to
-// code 2.  Border rule of backtrace: column 0 -> code 1, row 0 -> code 2.
+// code 2 (even when that is not the minimum).  Border rule of backtrace: column 0 -> code 1,
+// row 0 -> code 2.
 #include "common.cuh"
 
 namespace wca {
 
-constexpr int kCellsPerWord = 16;  // 2-bit codes
+constexpr int kDtwWarps = 4;  // problems per CTA
 
-__host__ __device__ inline int trace_words_per_row(int M) {
-    int w = (M + kCellsPerWord - 1) / kCellsPerWord;
-    return w | 1;  // odd stride: neighbouring rows land in different banks
-}
+template <int R> struct TraceWord { using type = uint64_t; };
+template <> struct TraceWord<1> { using type = uint8_t; };
+template <> struct TraceWord<2> { using type = uint8_t; };
+template <> struct TraceWord<4> { using type = uint8_t; };
+template <> struct TraceWord<8> { using type = uint16_t; };
+template <> struct TraceWord<16> { using type = uint32_t; };
 
 struct DtwLaunch {
     const float *matrix;
     const wca_utt_t *utts;
+    int n_utts;
     int negate;
     int32_t *path_text, *path_time, *path_len, *jump_frames;
     const int32_t *word_bounds;
     double *start_times, *end_times;
-    uint32_t *trace_ws;       // global fallback, trace_ws_stride words per problem
-    int64_t trace_ws_stride;  // 0 => trace lives in shared memory
+    unsigned char *trace_ws;   // global fallback, trace_stride bytes per problem
+    int64_t trace_stride;      // bytes of trace per problem (shared or global)
+    int jump_stride;           // ints of jump buffer per problem in shared memory
+    int trace_in_smem;
 };
 
-template <bool kOneWarp>
-__device__ __forceinline__ void step_barrier() {
-    if constexpr (kOneWarp) __syncwarp();
-    else __syncthreads();
-}
-
-template <bool kOneWarp>
-__global__ void __launch_bounds__(1024) dtw_align_kernel(const DtwLaunch p) {
+template <int R>
+__global__ void __launch_bounds__(kDtwWarps * 32) dtw_align_kernel(const DtwLaunch p) {
+    using Word = typename TraceWord<R>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const wca_utt_t u = p.utts[blockIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int prob = blockIdx.x * kDtwWarps + warp;
+    if (prob >= p.n_utts) return;  // whole warp
+    const wca_utt_t u = p.utts[prob];
     const int N = u.row_end - u.row_begin;
     const int M = u.n_frames;
-    const int nthr = blockDim.x;
-    const int tid = threadIdx.x;
 
-    float *line = reinterpret_cast<float *>(smem_raw);                 // [2][nthr + 1]
-    int32_t *jump_s = reinterpret_cast<int32_t *>(line + 2 * (nthr + 1));  // [nthr]
-    uint32_t *trace = p.trace_ws_stride ? p.trace_ws + (int64_t)blockIdx.x * p.trace_ws_stride
-                                        : reinterpret_cast<uint32_t *>(jump_s + nthr);
-    const int wpr = trace_words_per_row(M);
-
+    int32_t *jump_s = reinterpret_cast<int32_t *>(smem_raw) + warp * p.jump_stride;
+    Word *trace = p.trace_in_smem
+                      ? reinterpret_cast<Word *>(smem_raw + (size_t)kDtwWarps * p.jump_stride * 4 + (size_t)warp * p.trace_stride)
+                      : reinterpret_cast<Word *>(p.trace_ws + (size_t)prob * p.trace_stride);
     if (N <= 0 || M <= 0) {
-        if (tid == 0 && p.path_len) p.path_len[blockIdx.x] = 0;
+        if (lane == 0 && p.path_len) p.path_len[prob] = 0;
         return;
     }
+    for (int r = lane; r < N; r += 32) jump_s[r] = -1;
 
-    // ---- forward sweep ---------------------------------------------------------
-    const int i = tid + 1;  // table row
-    const bool row_live = i <= N;
-    const float *xrow = p.matrix + u.matrix_off + (int64_t)(row_live ? i - 1 : 0) * M;
-    for (int k = tid; k < 2 * (nthr + 1); k += nthr) line[k] = INFINITY;  // row 0 border and idle slots
-    jump_s[tid] = -1;
-    float left = INFINITY;                         // cost[i][j-1], starts at cost[i][0]
-    float upleft = (i == 1) ? 0.f : INFINITY;      // cost[i-1][j-1], starts at cost[i-1][0]
-    uint32_t tw = 0;
-    step_barrier<kOneWarp>();
-
-    auto load_x = [&](int s) -> float {
-        const int j = s - i;
-        if (!row_live || j < 1 || j > M) return 0.f;
-        const float v = xrow[j - 1];
-        return p.negate ? -v : v;
-    };
-
-    const int s_last = N + M;
-    float xc[4], xn[4];
+    // ---- forward sweep: lane l handles table rows l*R+1 .. l*R+R, column j = step - l + 1 ------
+    const float *x = p.matrix + u.matrix_off;
+    const int row0 = lane * R;  // first 0-based matrix row of the strip
+    float left[R];              // cost[i][j-1] of the strip rows, starts at cost[i][0] = inf
 #pragma unroll
-    for (int q = 0; q < 4; ++q) xc[q] = load_x(2 + q);
-    for (int s0 = 2; s0 <= s_last; s0 += 4) {
+    for (int r = 0; r < R; ++r) left[r] = INFINITY;
+    float diag_top = (lane == 0) ? 0.f : INFINITY;  // cost[row above strip][j-1]; cost[0][0] = 0 for lane 0
+    float xn[R];
+    auto load_col = [&](int j, float (&dst)[R]) {  // x[row][j-1] for the strip, 0 outside
 #pragma unroll
-        for (int q = 0; q < 4; ++q) xn[q] = load_x(s0 + 4 + q);  // in flight while this group runs
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int s = s0 + q;
-            if (s <= s_last) {  // uniform across the CTA
-                const int j = s - i;
-                if (row_live && j >= 1 && j <= M) {
-                    const float up = line[((s - 1) & 1) * (nthr + 1) + (i - 1)];  // cost[i-1][j]
-                    const float c0 = upleft, c1 = up, c2 = left;
-                    float c;
-                    uint32_t code;
-                    if (c0 < c1 && c0 < c2) {
-                        c = c0;
-                        code = 0u;
-                    } else if (c1 < c0 && c1 < c2) {
-                        c = c1;
-                        code = 1u;
-                    } else {
-                        c = c2;
-                        code = 2u;
-                    }
-                    const float cost = __fadd_rn(xc[q], c);
-                    line[(s & 1) * (nthr + 1) + i] = cost;
-                    upleft = up;
-                    left = cost;
-                    const int cell = (j - 1) & (kCellsPerWord - 1);
-                    tw |= code << (2 * cell);
-                    if (cell == kCellsPerWord - 1 || j == M) {
-                        trace[(int64_t)(i - 1) * wpr + ((j - 1) >> 4)] = tw;
-                        tw = 0;
-                    }
-                }
-                step_barrier<kOneWarp>();
-            }
+        for (int r = 0; r < R; ++r) {
+            const int row = row0 + r;
+            float v = 0.f;
+            if (row < N && j >= 1 && j <= M) v = x[(int64_t)row * M + (j - 1)];
+            dst[r] = p.negate ? -v : v;
         }
+    };
+    load_col(1 - lane, xn);
+    const int n_steps = M + 31;
+    for (int s = 0; s < n_steps; ++s) {
+        const int j = s - lane + 1;
+        // bottom row of the strip above, as of the previous step (= its column j): cost[row0][j]
+        float up_top = __shfl_up_sync(0xffffffffu, left[R - 1], 1);
+        if (lane == 0) up_top = INFINITY;  // cost[0][j], j >= 1
+        float xc[R];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) xc[q] = xn[q];
+        for (int r = 0; r < R; ++r) xc[r] = xn[r];
+        load_col(j + 1, xn);  // next column in flight while this one is computed
+        if (j >= 1 && j <= M) {
+            Word tw = 0;
+            float c0 = diag_top;  // cost[i-1][j-1]
+            float c1 = up_top;    // cost[i-1][j]
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float c2 = left[r];  // cost[i][j-1]
+                float c;
+                uint32_t code;
+                if (c0 < c1 && c0 < c2) {
+                    c = c0;
+                    code = 0u;
+                } else if (c1 < c0 && c1 < c2) {
+                    c = c1;
+                    code = 1u;
+                } else {
+                    c = c2;
+                    code = 2u;
+                }
+                const float cost = __fadd_rn(xc[r], c);
+                tw |= (Word)((Word)code << (2 * (r % (4 * (int)sizeof(Word)))));
+                c0 = c2;    // this row's old value is the next row's diagonal
+                c1 = cost;  // this row's new value is the next row's "up"
+                left[r] = cost;
+            }
+            diag_top = up_top;
+            trace[(int64_t)(j - 1) * 32 + lane] = tw;
+        }
     }
-    __syncthreads();  // trace complete (global fallback: same-CTA visibility is enough)
+    __syncwarp();
 
-    // ---- backtrace (sequential by nature) ------------------------------------------
-    if (tid == 0) {
+    // ---- backtrace (sequential by nature), lane 0 ---------------------------------------------
+    if (lane == 0) {
         const int cap = N + M;
         int32_t *pt = p.path_text ? p.path_text + u.path_off : nullptr;
         int32_t *pj = p.path_time ? p.path_time + u.path_off : nullptr;
@@ -140,9 +139,13 @@ __global__ void __launch_bounds__(1024) dtw_align_kernel(const DtwLaunch p) {
             uint32_t code;
             if (bj == 0) code = 1u;
             else if (bi == 0) code = 2u;
-            else code = (trace[(int64_t)(bi - 1) * wpr + ((bj - 1) >> 4)] >> (2 * ((bj - 1) & 15))) & 3u;
+            else {
+                const int row = bi - 1;
+                const Word w = trace[(int64_t)(bj - 1) * 32 + row / R];
+                code = (uint32_t)(w >> (2 * (row % R))) & 3u;
+            }
             // first path point of a text row: the step out of it changes the row (or ends the walk)
-            if ((code != 2u || (bi == 0 && bj == 1)) && bi >= 1) jump_s[bi - 1] = bj - 1;
+            if (code != 2u && bi >= 1) jump_s[bi - 1] = bj - 1;
             if (code == 0u) {
                 --bi;
                 --bj;
@@ -152,34 +155,53 @@ __global__ void __launch_bounds__(1024) dtw_align_kernel(const DtwLaunch p) {
                 --bj;
             }
         }
-        if (p.path_len) p.path_len[blockIdx.x] = cap - pos;
+        if (p.path_len) p.path_len[prob] = cap - pos;
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- jump frames and word times (timing.py:110-113) ----------------------------
+    // ---- jump frames and word times (timing.py:110-113) ----------------------------------------
     if (p.jump_frames)
-        for (int r = tid; r < N; r += nthr) p.jump_frames[u.jump_off + r] = jump_s[r];
+        for (int r = lane; r < N; r += 32) p.jump_frames[u.jump_off + r] = jump_s[r];
     if (p.word_bounds && p.start_times && p.end_times) {
         const int32_t *wb = p.word_bounds + u.word_off;
-        for (int w = tid; w < u.n_words; w += nthr) {
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        for (int w = lane; w < u.n_words; w += 32) {
             const int a = wb[w], b = wb[w + 1];
-            const double nan = __longlong_as_double(0x7ff8000000000000ll);
             p.start_times[u.word_off + w] = (a >= 0 && a < N) ? (double)jump_s[a] / WCA_TOKENS_PER_SECOND : nan;
             p.end_times[u.word_off + w] = (b >= 0 && b < N) ? (double)jump_s[b] / WCA_TOKENS_PER_SECOND : nan;
         }
     }
 }
 
-static size_t dtw_fixed_smem(int nthr) { return (size_t)(2 * (nthr + 1) + nthr) * 4u; }
+static int strip_rows(int max_rows) {
+    int r = 1;
+    while (r * 32 < max_rows) r *= 2;
+    return r;  // 1, 2, 4, 8, 16, 32
+}
+static size_t trace_word_bytes(int r) { return r <= 4 ? 1 : (r == 8 ? 2 : (r == 16 ? 4 : 8)); }
 static size_t dtw_trace_bytes(int max_rows, int max_frames) {
-    return (size_t)max_rows * trace_words_per_row(max_frames) * 4u;
+    const size_t b = (size_t)max_frames * 32 * trace_word_bytes(strip_rows(max_rows));
+    return (b + 15) & ~(size_t)15;
 }
 constexpr size_t kSmemBudget = 227u * 1024u;
 
+static bool dtw_fits_smem(int max_rows, int max_frames) {
+    return kDtwWarps * ((size_t)max_rows * 4 + dtw_trace_bytes(max_rows, max_frames)) <= kSmemBudget;
+}
+
 int64_t dtw_workspace_bytes(int n_utts, int max_rows, int max_frames) {
-    const int nthr = ((max_rows + 31) / 32) * 32;
-    if (dtw_fixed_smem(nthr) + dtw_trace_bytes(max_rows, max_frames) <= kSmemBudget) return 0;
+    if (dtw_fits_smem(max_rows, max_frames)) return 0;
     return (int64_t)n_utts * (int64_t)dtw_trace_bytes(max_rows, max_frames);
+}
+
+template <int R>
+static int launch_r(const DtwLaunch &p, size_t smem, cudaStream_t stream) {
+    if (smem > 48u * 1024u)
+        WCA_CUDA(cudaFuncSetAttribute(dtw_align_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (p.n_utts + kDtwWarps - 1) / kDtwWarps;
+    dtw_align_kernel<R><<<grid, kDtwWarps * 32, smem, stream>>>(p);
+    WCA_LAUNCH_CHECK("dtw_align_kernel");
+    return WCA_OK;
 }
 
 int launch_dtw_align(const float *d_matrix, const wca_utt_t *d_utts, int n_utts, int max_rows, int max_frames,
@@ -187,13 +209,15 @@ int launch_dtw_align(const float *d_matrix, const wca_utt_t *d_utts, int n_utts,
                      int32_t *d_jump_frames, const int32_t *d_word_bounds, double *d_start_times,
                      double *d_end_times, void *d_trace_ws, int64_t trace_ws_bytes, cudaStream_t stream) {
     if (max_rows > 1024) {
-        set_error("wca_dtw_align: %d text rows exceed the 1024 rows one CTA sweeps (Whisper caps T at 448)", max_rows);
+        set_error("wca_dtw_align: %d text rows exceed the 1024 rows one warp sweeps (Whisper caps T at 448)", max_rows);
         return WCA_ERR_UNSUPPORTED;
     }
-    const int nthr = max_rows <= 0 ? 32 : ((max_rows + 31) / 32) * 32;
+    if (max_rows < 1) max_rows = 1;
+    if (max_frames < 1) max_frames = 1;
     DtwLaunch p;
     p.matrix = d_matrix;
     p.utts = d_utts;
+    p.n_utts = n_utts;
     p.negate = negate;
     p.path_text = d_path_text;
     p.path_time = d_path_time;
@@ -203,32 +227,29 @@ int launch_dtw_align(const float *d_matrix, const wca_utt_t *d_utts, int n_utts,
     p.start_times = d_start_times;
     p.end_times = d_end_times;
     p.trace_ws = nullptr;
-    p.trace_ws_stride = 0;
-    size_t smem = dtw_fixed_smem(nthr);
-    const size_t trace_bytes = dtw_trace_bytes(max_rows > 0 ? max_rows : 1, max_frames > 0 ? max_frames : 1);
-    if (smem + trace_bytes <= kSmemBudget) {
-        smem += trace_bytes;
+    p.trace_stride = (int64_t)dtw_trace_bytes(max_rows, max_frames);
+    p.jump_stride = (max_rows + 3) & ~3;
+    p.trace_in_smem = dtw_fits_smem(max_rows, max_frames) ? 1 : 0;
+    size_t smem = (size_t)kDtwWarps * p.jump_stride * 4;
+    if (p.trace_in_smem) {
+        smem += (size_t)kDtwWarps * p.trace_stride;
     } else {
-        const int64_t need = (int64_t)n_utts * (int64_t)trace_bytes;
+        const int64_t need = (int64_t)n_utts * p.trace_stride;
         if (!d_trace_ws || trace_ws_bytes < need) {
             set_error("wca_dtw_align: trace workspace of %lld bytes required, %lld given", (long long)need,
                       (long long)trace_ws_bytes);
             return WCA_ERR_INVALID;
         }
-        p.trace_ws = static_cast<uint32_t *>(d_trace_ws);
-        p.trace_ws_stride = (int64_t)(trace_bytes / 4u);
+        p.trace_ws = static_cast<unsigned char *>(d_trace_ws);
     }
-    if (nthr == 32) {
-        if (smem > 48u * 1024u)
-            WCA_CUDA(cudaFuncSetAttribute(dtw_align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dtw_align_kernel<true><<<n_utts, nthr, smem, stream>>>(p);
-    } else {
-        if (smem > 48u * 1024u)
-            WCA_CUDA(cudaFuncSetAttribute(dtw_align_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dtw_align_kernel<false><<<n_utts, nthr, smem, stream>>>(p);
+    switch (strip_rows(max_rows)) {
+        case 1: return launch_r<1>(p, smem, stream);
+        case 2: return launch_r<2>(p, smem, stream);
+        case 4: return launch_r<4>(p, smem, stream);
+        case 8: return launch_r<8>(p, smem, stream);
+        case 16: return launch_r<16>(p, smem, stream);
+        default: return launch_r<32>(p, smem, stream);
     }
-    WCA_LAUNCH_CHECK("dtw_align_kernel");
-    return WCA_OK;
 }
 
 }  // namespace wca
