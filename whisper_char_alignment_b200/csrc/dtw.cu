@@ -8,9 +8,12 @@
 // exchange per step is one __shfl_up (the bottom row of the strip above), there is no block
 // barrier, and a 128-thread CTA runs four independent problems, so a batch of small
 // problems (BASELINE config 2: 41 x 150; config 5: 384 heads per utterance) fills the SMs
-// with independent dependency chains.  The trace is 2 bits per cell, packed per (column,
-// lane) word and kept in shared memory (global workspace only when a problem does not fit);
-// lane 0 backtraces on the device and only N jump frames / W word times leave the SM.
+// with independent dependency chains.  The cost matrix is first staged into shared memory
+// with coalesced loads (negated on the way) whenever it fits next to the trace, so no global
+// load sits on the step-to-step dependency chain; larger problems read their columns
+// directly.  The trace is 2 bits per cell, packed per (column, lane) word and kept in shared
+// memory (global workspace only when a problem does not fit); lane 0 backtraces on the device
+// and only N jump frames / W word times leave the SM.
 //
 // Bit-exactness contract (must match dtw_cpu): fp32 round-to-nearest add, no FMA; the
 // diagonal wins only if strictly smaller than both others, then the text step only if
@@ -21,7 +24,6 @@
 
 namespace wca {
 
-constexpr int kDtwWarps = 4;  // problems per CTA
 
 template <int R> struct TraceWord { using type = uint64_t; };
 template <> struct TraceWord<1> { using type = uint8_t; };
@@ -42,31 +44,49 @@ struct DtwLaunch {
     int64_t trace_stride;      // bytes of trace per problem (shared or global)
     int jump_stride;           // ints of jump buffer per problem in shared memory
     int trace_in_smem;
+    int stage_floats;          // floats of staged cost matrix per problem in shared memory (0: read global)
+    int warps;                 // problems per CTA
 };
 
 template <int R>
-__global__ void __launch_bounds__(kDtwWarps * 32) dtw_align_kernel(const DtwLaunch p) {
+__global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
     using Word = typename TraceWord<R>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int prob = blockIdx.x * kDtwWarps + warp;
+    const int prob = blockIdx.x * p.warps + warp;
     if (prob >= p.n_utts) return;  // whole warp
     const wca_utt_t u = p.utts[prob];
     const int N = u.row_end - u.row_begin;
     const int M = u.n_frames;
 
+    // shared memory: [jump buffers][traces][staged matrices], one slice per warp
     int32_t *jump_s = reinterpret_cast<int32_t *>(smem_raw) + warp * p.jump_stride;
-    Word *trace = p.trace_in_smem
-                      ? reinterpret_cast<Word *>(smem_raw + (size_t)kDtwWarps * p.jump_stride * 4 + (size_t)warp * p.trace_stride)
-                      : reinterpret_cast<Word *>(p.trace_ws + (size_t)prob * p.trace_stride);
+    unsigned char *after_jump = smem_raw + (size_t)p.warps * p.jump_stride * 4;
+    Word *trace = p.trace_in_smem ? reinterpret_cast<Word *>(after_jump + (size_t)warp * p.trace_stride)
+                                  : reinterpret_cast<Word *>(p.trace_ws + (size_t)prob * p.trace_stride);
+    float *xs = reinterpret_cast<float *>(after_jump + (p.trace_in_smem ? (size_t)p.warps * p.trace_stride : 0)) +
+                (size_t)warp * p.stage_floats;
     if (N <= 0 || M <= 0) {
         if (lane == 0 && p.path_len) p.path_len[prob] = 0;
         return;
     }
     for (int r = lane; r < N; r += 32) jump_s[r] = -1;
 
+    // ---- stage the cost matrix (coalesced, sign applied once) -----------------------------------
+    const float *xg = p.matrix + u.matrix_off;
+    const bool staged = p.stage_floats > 0;
+    if (staged) {
+        const int total = N * M;
+        for (int e = lane; e < total; e += 32) {
+            const float v = xg[e];
+            xs[e] = p.negate ? -v : v;
+        }
+        __syncwarp();
+    }
+    const float *x = staged ? xs : xg;
+    const bool flip = p.negate && !staged;
+
     // ---- forward sweep: lane l handles table rows l*R+1 .. l*R+R, column j = step - l + 1 ------
-    const float *x = p.matrix + u.matrix_off;
     const int row0 = lane * R;  // first 0-based matrix row of the strip
     float left[R];              // cost[i][j-1] of the strip rows, starts at cost[i][0] = inf
 #pragma unroll
@@ -79,7 +99,7 @@ __global__ void __launch_bounds__(kDtwWarps * 32) dtw_align_kernel(const DtwLaun
             const int row = row0 + r;
             float v = 0.f;
             if (row < N && j >= 1 && j <= M) v = x[(int64_t)row * M + (j - 1)];
-            dst[r] = p.negate ? -v : v;
+            dst[r] = flip ? -v : v;
         }
     };
     load_col(1 - lane, xn);
@@ -185,12 +205,34 @@ static size_t dtw_trace_bytes(int max_rows, int max_frames) {
 }
 constexpr size_t kSmemBudget = 227u * 1024u;
 
-static bool dtw_fits_smem(int max_rows, int max_frames) {
-    return kDtwWarps * ((size_t)max_rows * 4 + dtw_trace_bytes(max_rows, max_frames)) <= kSmemBudget;
+// Shared-memory plan for a launch: problems per CTA, whether the trace and the staged matrix fit.
+struct DtwPlan {
+    int warps, trace_in_smem, stage_floats;
+    size_t smem;
+};
+static DtwPlan dtw_plan(int max_rows, int max_frames) {
+    const size_t jump = (size_t)((max_rows + 3) & ~3) * 4;
+    const size_t trace = dtw_trace_bytes(max_rows, max_frames);
+    const size_t stage = (((size_t)max_rows * max_frames + 3) & ~(size_t)3) * 4;
+    DtwPlan pl;
+    for (int warps = 4; warps >= 1; warps >>= 1) {  // prefer everything on chip, then more problems per CTA
+        if (warps * (jump + trace + stage) <= kSmemBudget) {
+            pl = {warps, 1, (int)(stage / 4), warps * (jump + trace + stage)};
+            return pl;
+        }
+    }
+    for (int warps = 4; warps >= 1; warps >>= 1) {
+        if (warps * (jump + trace) <= kSmemBudget) {
+            pl = {warps, 1, 0, warps * (jump + trace)};
+            return pl;
+        }
+    }
+    pl = {4, 0, 0, 4 * jump};
+    return pl;
 }
 
 int64_t dtw_workspace_bytes(int n_utts, int max_rows, int max_frames) {
-    if (dtw_fits_smem(max_rows, max_frames)) return 0;
+    if (dtw_plan(max_rows, max_frames).trace_in_smem) return 0;
     return (int64_t)n_utts * (int64_t)dtw_trace_bytes(max_rows, max_frames);
 }
 
@@ -198,8 +240,8 @@ template <int R>
 static int launch_r(const DtwLaunch &p, size_t smem, cudaStream_t stream) {
     if (smem > 48u * 1024u)
         WCA_CUDA(cudaFuncSetAttribute(dtw_align_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (p.n_utts + kDtwWarps - 1) / kDtwWarps;
-    dtw_align_kernel<R><<<grid, kDtwWarps * 32, smem, stream>>>(p);
+    const int grid = (p.n_utts + p.warps - 1) / p.warps;
+    dtw_align_kernel<R><<<grid, p.warps * 32, smem, stream>>>(p);
     WCA_LAUNCH_CHECK("dtw_align_kernel");
     return WCA_OK;
 }
@@ -229,11 +271,12 @@ int launch_dtw_align(const float *d_matrix, const wca_utt_t *d_utts, int n_utts,
     p.trace_ws = nullptr;
     p.trace_stride = (int64_t)dtw_trace_bytes(max_rows, max_frames);
     p.jump_stride = (max_rows + 3) & ~3;
-    p.trace_in_smem = dtw_fits_smem(max_rows, max_frames) ? 1 : 0;
-    size_t smem = (size_t)kDtwWarps * p.jump_stride * 4;
-    if (p.trace_in_smem) {
-        smem += (size_t)kDtwWarps * p.trace_stride;
-    } else {
+    const DtwPlan pl = dtw_plan(max_rows, max_frames);
+    p.trace_in_smem = pl.trace_in_smem;
+    p.stage_floats = pl.stage_floats;
+    p.warps = pl.warps;
+    const size_t smem = pl.smem;
+    if (!p.trace_in_smem) {
         const int64_t need = (int64_t)n_utts * p.trace_stride;
         if (!d_trace_ws || trace_ws_bytes < need) {
             set_error("wca_dtw_align: trace workspace of %lld bytes required, %lld given", (long long)need,
