@@ -77,8 +77,9 @@ __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
     const bool staged = p.stage_floats > 0;
     if (staged) {
         const int total = N * M;
-        for (int e = lane; e < total; e += 32) {
-            const float v = xg[e];
+#pragma unroll 8
+        for (int e = lane; e < total; e += 32) {  // independent loads: eight rows of requests in flight per lane
+            const float v = ld_stream(xg + e);
             xs[e] = p.negate ? -v : v;
         }
         __syncwarp();
