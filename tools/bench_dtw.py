@@ -33,7 +33,7 @@ def run(label, n_prob, N, M, reps=5):
     want = odtw.jump_frames(ti, tj)
     assert np.array_equal(jumps[:N].cpu().numpy(), want), "jump frames differ from the oracle"
     cells = n_prob * N * M
-    print(f"{label:34s} {n_prob:5d} x ({N:3d} x {M:4d}): {ms*1e3:9.1f} us/launch  {cells/ms/1e3/1e6:9.1f} Mcells/s   "
+    print(f"{label:34s} {n_prob:5d} x ({N:3d} x {M:4d}): {ms*1e3:9.1f} us/launch  {cells/ms/1e6:9.2f} Gcells/s   "
           f"(C oracle, 1 core: {N*M/cpu_s/1e6:6.1f} Mcells/s; trace ws {nbytes} B)", flush=True)
 
 run("config 2, one batch of 16", 16, 41, 150)
