@@ -101,6 +101,22 @@ def main():
         np.savez_compressed(os.path.join(OUT, c["name"] + ".npz"), **out)
         print(c["name"], out["weights"].shape, "sentinel" if out["sentinel"] else (out["start_times"], out["end_times"]))
 
+    # default_find_alignment (timing.py:116-186): stock-Whisper baseline on the alignment heads
+    for n, c in enumerate([
+        dict(name="default_micro_sub", model="micro", text="stock whisper timing path", unit="subword", frames=120, width=7, qk_scale=1.0),
+        dict(name="default_mini_char", model="mini", text="alignment heads only", unit="char", frames=160, width=7, qk_scale=1.0),
+    ]):
+        model = make_model(c["model"], 0, 4.0)
+        mel = make_mel(model.dims.n_mels, 2 * model.dims.n_audio_ctx, 2 * c["frames"], seed=300 + n)
+        text_tokens = ref_retok.encode(c["text"], tk, c["unit"])
+        words, st, en, weights, _ = ref_timing.default_find_alignment(model, tk, text_tokens, mel, c["frames"],
+                                                                     medfilt_width=c["width"], qk_scale=c["qk_scale"])
+        np.savez_compressed(os.path.join(OUT, c["name"] + ".npz"), mel=mel.numpy(),
+                            text_tokens=np.array(text_tokens, dtype=np.int64), weights=weights.numpy(), start_times=st,
+                            end_times=en, words=np.array(json.dumps(words)), case=np.array(json.dumps(c)),
+                            sentinel=np.array(False))
+        print(c["name"], weights.shape, st, en)
+
     # C1: sample/test.wav (NIST SPHERE, 46592 samples -> 145 frames), Whisper-base dims,
     # README.md:76-140 settings: char units, topk=10, medfilt_width=3.
     pcm = sphere_pcm(os.path.join(REF, "sample", "test.wav"))

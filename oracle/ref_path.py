@@ -193,3 +193,28 @@ def force_align(ws, tokens, tokenizer, aligned_unit_type="subword", aggregation=
         return [[], [], [], [], None]  # :106-107, a LIST
     start_times, end_times, _ = boundaries_from_path(text_indices, time_indices, word_tokens)
     return words, start_times, end_times, matrix, scores
+
+
+# --------------------------------------------------------------------------
+# default_find_alignment, timing.py:116-186 (the stock-Whisper baseline behind
+# --default_whisper_timing, infer_ali.py:83-85)
+# --------------------------------------------------------------------------
+def default_find_alignment(model, tokenizer, text_tokens, mel, max_frames, *, medfilt_width=7, qk_scale=1.0):
+    """Only `model.alignment_heads` (:156), filtered softmax (:157-159), std/mean normalisation over
+    tokens (:160-161), mean over heads (:163), DTW (:165) -- on the CPU recurrence, which is the
+    parity target -- and word grouping with the tokenizer's own split_to_word_tokens (:167)."""
+    tokens = torch.tensor([*tokenizer.sot_sequence, tokenizer.no_timestamps, *text_tokens, tokenizer.eot])
+    qk, _ = capture_logits(model, mel, tokens)  # (L, H, T, n_ctx)
+    heads = model.alignment_heads.indices().T
+    weights = torch.stack([qk[l][h] for l, h in heads])[:, :, :max_frames]
+    weights = median_along_frames(weights, medfilt_width)
+    weights = (weights * qk_scale).softmax(dim=-1)
+    std, mean = torch.std_mean(weights, dim=-2, keepdim=True, unbiased=False)
+    weights = (weights - mean) / std
+    matrix = weights.mean(axis=0)[len(tokenizer.sot_sequence):-1]
+    text_indices, time_indices = _dtw.dtw_path((-matrix).numpy())
+    words, word_tokens = tokenizer.split_to_word_tokens(list(text_tokens) + [tokenizer.eot])
+    if len(word_tokens) <= 1:
+        return [[], [], [], [], None]
+    start_times, end_times, _ = boundaries_from_path(text_indices, time_indices, word_tokens)
+    return words, start_times, end_times, weights, None

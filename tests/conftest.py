@@ -27,7 +27,12 @@ def pytest_collection_modifyitems(config, items):
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+    """Fixtures of get_attentions + force_align (the default_find_alignment ones are listed separately)."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("default_"))
+
+
+def default_timing_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.startswith("default_") and f.endswith(".npz"))
 
 
 def load_golden(name):

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_names, load_golden
+from conftest import default_timing_names, golden_names, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -304,3 +304,23 @@ def test_batched_path_equals_single_utterance_path(timing, tokenizer, oracle_mod
         np.testing.assert_array_equal(r[1], one[1])
         np.testing.assert_array_equal(r[2], one[2])
         assert torch.equal(r[3], one[3])
+
+
+@pytest.mark.parametrize("name", default_timing_names())
+def test_default_find_alignment_against_reference_fixture(name, timing, tokenizer, oracle_models, dev):
+    """timing.py:116-186 (stock-Whisper baseline): normalised alignment-head maps and word boundaries."""
+    g = load_golden(name)
+    c = g["case"]
+    model = product_model(oracle_models(c["model"]), dev)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        words, st, en, weights, none = timing.default_find_alignment(
+            model, tokenizer, g["text_tokens"].tolist(), torch.from_numpy(g["mel"]).to(dev), c["frames"],
+            medfilt_width=c["width"], qk_scale=c["qk_scale"])
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert none is None and words == g["words"]
+    torch.testing.assert_close(weights.cpu(), torch.from_numpy(g["weights"]), rtol=2e-3, atol=2e-4)
+    np.testing.assert_array_equal(np.round(st * 50).astype(int), np.round(g["start_times"] * 50).astype(int))
+    np.testing.assert_array_equal(np.round(en * 50).astype(int), np.round(g["end_times"] * 50).astype(int))

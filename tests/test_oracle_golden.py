@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_names, load_golden
+from conftest import default_timing_names, golden_names, load_golden
 from oracle import dtw as odtw
 from oracle import ref_path
 
@@ -108,3 +108,17 @@ def test_median_restatement_matches_scipy():
         size = [1] * (x.ndim - 1) + [width]
         want = sp_median(x.numpy(), size=size, mode="mirror")  # scipy 'mirror' == torch 'reflect'
         np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", default_timing_names())
+def test_default_find_alignment_restatement(name, oracle_models, tokenizer):
+    g = load_golden(name)
+    c = g["case"]
+    model = oracle_models(c["model"])
+    words, st, en, weights, none = ref_path.default_find_alignment(
+        model, tokenizer, g["text_tokens"].tolist(), torch.from_numpy(g["mel"]), c["frames"],
+        medfilt_width=c["width"], qk_scale=c["qk_scale"])
+    assert none is None and words == g["words"]
+    np.testing.assert_allclose(weights.numpy(), g["weights"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_array_equal(st, g["start_times"])
+    np.testing.assert_array_equal(en, g["end_times"])

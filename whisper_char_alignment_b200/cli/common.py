@@ -1,0 +1,80 @@
+"""Shared plumbing of the CLI shells: model/tokenizer loading, transcript source, batching."""
+from __future__ import annotations
+
+import datetime
+import json
+import os
+import time
+
+import torch
+
+from .. import audio, whisper_model
+from ..retokenize import encode, remove_punctuation
+from ..tokenizer import get_tokenizer as byte_tokenizer
+
+MAX_FRAMES = 1500  # reference infer_ali.py:25
+MAX_LENGTH = 448   # reference infer_ali.py:26
+AUDIO_SAMPLES_PER_TOKEN = audio.N_SAMPLES_PER_TOKEN  # reference infer_ali.py:179
+
+TEST_SIZES = {  # tiny dims for smoke runs, same head width as the published models
+    "micro": (80, 256, 128, 2, 2, 51865, 448, 128, 2, 2),
+    "mini": (80, 512, 256, 4, 2, 51865, 448, 256, 4, 3),
+}
+
+
+def load_model_and_tokenizer(name: str, device, qk_gain: float = 4.0):
+    """Stock `openai-whisper` when it is installed (real checkpoints, real tokenizer, greedy
+    decode available); otherwise a checkpoint path or a seeded random-init model of the named
+    size with the offline byte tokenizer."""
+    try:
+        import whisper  # noqa: F401
+        from whisper.tokenizer import get_tokenizer
+
+        model = whisper.load_model(name).to(device)
+        return model, get_tokenizer(model.is_multilingual, language="English"), whisper
+    except ImportError:
+        if name in TEST_SIZES:
+            model = whisper_model.random_init(whisper_model.ModelDimensions(*TEST_SIZES[name]), qk_gain=qk_gain).to(device)
+        else:
+            model = whisper_model.load_model(name, device, qk_gain=qk_gain)
+        return model, byte_tokenizer(model.is_multilingual, language="English"), None
+
+
+def transcribe(whisper_pkg, model, mel, reference_text: str) -> str:
+    """The reference transcribes with whisper.decode (infer_ali.py:60); that autoregressive step is
+    upstream and out of scope, so offline the reference transcript is force-aligned instead."""
+    if whisper_pkg is None:
+        return reference_text
+    return whisper_pkg.decode(model, mel, whisper_pkg.DecodingOptions(language="en")).text
+
+
+def prepare(record, tokenizer, unit, device, whisper_pkg, model):
+    """One dataset record -> dict with tokens and frame count, or None when the reference would skip it
+    (infer_ali.py:78-81)."""
+    _, mel, duration, text, starts, ends, fid = record
+    mel = mel.to(device)
+    text = remove_punctuation(text)
+    transcription = remove_punctuation(transcribe(whisper_pkg, model, mel, text)) or " "
+    text_tokens = encode(transcription, tokenizer, unit)
+    tokens = torch.tensor([*tokenizer.sot_sequence, tokenizer.no_timestamps, *text_tokens, tokenizer.eot], device=device)
+    max_frames = int(duration) // AUDIO_SAMPLES_PER_TOKEN
+    if max_frames > MAX_FRAMES or len(tokens) > MAX_LENGTH or max_frames < 1:
+        print(fid)
+        return None
+    return dict(mel=mel, tokens=tokens, text_tokens=text_tokens, max_frames=max_frames, text=text, starts=starts,
+                ends=ends, fid=fid)
+
+
+def batches(items, size):
+    for i in range(0, len(items), size):
+        yield items[i:i + size]
+
+
+def dump_results(args, results: dict):
+    """<output_dir>/<%Y-%m-%d-%H:%M:%S>.json = flags merged with metrics (reference infer_ali.py:139-146)."""
+    stamp = datetime.datetime.fromtimestamp(time.time()).strftime("%Y-%m-%d-%H:%M:%S")
+    os.makedirs(args.output_dir, exist_ok=True)
+    path = os.path.join(args.output_dir, stamp + ".json")
+    with open(path, "w") as f:
+        json.dump({**vars(args), **results}, f)
+    return path, stamp

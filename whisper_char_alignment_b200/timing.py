@@ -36,7 +36,7 @@ TOKENS_PER_SECOND = 50  # whisper.audio: SAMPLE_RATE // (HOP_LENGTH * 2)
 
 __all__ = [
     "get_attentions", "get_attentions_batch", "filter_attention", "force_align", "force_align_batch",
-    "dtw", "dtw_batch", "median_filter_softmax",
+    "dtw", "dtw_batch", "median_filter_softmax", "default_find_alignment",
 ]
 
 
@@ -358,6 +358,29 @@ def force_align(ws, tokens, tokenizer, aligned_unit_type="subword", aggregation=
     when only EOT remains."""
     return force_align_batch([ws], [tokens], tokenizer, aligned_unit_type, aggregation, topk, w_colnorm, w_rownorm,
                              w_coverage)[0]
+
+
+def default_find_alignment(model, tokenizer, text_tokens, mel, max_frames, *, medfilt_width=7, qk_scale=1.0):
+    """Drop-in for reference timing.py:116-186 (the stock-Whisper baseline behind
+    `--default_whisper_timing`): only `model.alignment_heads`, std/mean normalisation over
+    tokens, mean over heads, DTW, words from `tokenizer.split_to_word_tokens`.
+    Returns (words, start_times, end_times, weights (heads, T, F) on the device, None).
+
+    Capture, filter, softmax, DTW and boundary extraction are the same kernels as the main
+    path; the head gather and the normalisation of the few selected maps are torch ops."""
+    device = mel.device
+    tokens = torch.tensor([*tokenizer.sot_sequence, tokenizer.no_timestamps, *text_tokens, tokenizer.eot], device=device)
+    maps, _ = get_attentions(mel, tokens, model, tokenizer, max_frames, medfilt_width, qk_scale)
+    n_heads = maps.shape[1]
+    picked = model.alignment_heads.indices().T.to(device)  # (n, 2) of (layer, head), timing.py:156
+    weights = maps.flatten(0, 1).index_select(0, picked[:, 0] * n_heads + picked[:, 1])
+    std, mean = torch.std_mean(weights, dim=-2, keepdim=True, unbiased=False)  # timing.py:160-161
+    weights = (weights - mean) / std
+    res = force_align(weights.mean(dim=0), list(text_tokens), tokenizer, "subword", "grad_norm")
+    if isinstance(res, list):
+        return res
+    words, start_times, end_times, _, _ = res
+    return words, start_times, end_times, weights, None
 
 
 # ---------------------------------------------------------------------------------
