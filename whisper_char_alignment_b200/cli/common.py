@@ -30,6 +30,8 @@ def load_model_and_tokenizer(name: str, device, qk_gain: float = 4.0):
         import whisper  # noqa: F401
         from whisper.tokenizer import get_tokenizer
 
+        if not (hasattr(whisper, "decode") and hasattr(whisper, "DecodingOptions")):
+            raise ImportError("a `whisper` module without decode() is not openai-whisper")
         model = whisper.load_model(name).to(device)
         return model, get_tokenizer(model.is_multilingual, language="English"), whisper
     except ImportError:
