@@ -16,9 +16,9 @@ MAX_FRAMES = 1500  # reference infer_ali.py:25
 MAX_LENGTH = 448   # reference infer_ali.py:26
 AUDIO_SAMPLES_PER_TOKEN = audio.N_SAMPLES_PER_TOKEN  # reference infer_ali.py:179
 
-TEST_SIZES = {  # tiny dims for smoke runs, same head width as the published models
-    "micro": (80, 256, 128, 2, 2, 51865, 448, 128, 2, 2),
-    "mini": (80, 512, 256, 4, 2, 51865, 448, 256, 4, 3),
+TEST_SIZES = {  # tiny dims for smoke runs: 30 s context and head width 64 like the published models
+    "micro": (80, 1500, 128, 2, 2, 51865, 448, 128, 2, 2),
+    "mini": (80, 1500, 256, 4, 2, 51865, 448, 256, 4, 3),
 }
 
 
