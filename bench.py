@@ -30,6 +30,39 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+
+
+def _preload_cublas_emulation():
+    """fp32 GEMMs of the upstream Whisper linears stay on cuBLAS (north_star); cuBLAS 12.9 can run
+    them as BF16x9-emulated fp32 on the tensor cores (CUBLAS_EMULATE_SINGLE_PRECISION) at fp32
+    accuracy.  torch 2.11+cu128 bundles cuBLAS 12.8, which predates that switch, so the CUDA
+    toolkit's 12.9 libraries of this image are mapped first (same SONAME: torch then binds to
+    them).  Must run before `import torch`.  Off with --fp32-gemm native / WCA_FP32_GEMM=native."""
+    mode = os.environ.get("WCA_FP32_GEMM", "")
+    for i, a in enumerate(sys.argv):
+        if a == "--fp32-gemm" and i + 1 < len(sys.argv):
+            mode = sys.argv[i + 1]
+        elif a.startswith("--fp32-gemm="):
+            mode = a.split("=", 1)[1]
+    if "--impl" in sys.argv and "reference" in sys.argv:
+        return "native"
+    if mode == "native":
+        return "native"
+    import ctypes
+
+    libdir = os.environ.get("WCA_CUBLAS_DIR", "/usr/local/cuda/lib64")
+    try:
+        os.environ.setdefault("CUBLAS_EMULATE_SINGLE_PRECISION", "1")
+        for name in ("libcublasLt.so.12", "libcublas.so.12"):
+            ctypes.CDLL(os.path.join(libdir, name), mode=ctypes.RTLD_GLOBAL)
+        return "bf16x9"
+    except OSError:
+        os.environ.pop("CUBLAS_EMULATE_SINGLE_PRECISION", None)
+        return "native"
+
+
+FP32_GEMM = _preload_cublas_emulation()
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -57,6 +90,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=16, help="utterances per step per GPU")
     ap.add_argument("--topk", type=int, default=10)
     ap.add_argument("--medfilt_width", type=int, default=3)
+    ap.add_argument("--fp32-gemm", default="bf16x9", choices=["bf16x9", "native"],
+                    help="cuBLAS fp32 GEMMs of the upstream linears: BF16x9-emulated fp32 (cuBLAS 12.9) or SIMT SGEMM")
     ap.add_argument("--cpu-sample", type=int, default=2, help="utterances timed for cpu_baseline (0 = skip)")
     return ap.parse_args()
 
@@ -69,6 +104,8 @@ def workload_config(args, world):
         "global_batch": args.batch * world,
         "parallelism": f"utterance sharding x{world}, no data-path collective; one final all_gather",
         "cache": "inputs larger than L2: each step streams the 3 GB fp32 weights and >1 GB of activations",
+        "fp32_gemm": ("cuBLAS 12.9 BF16x9-emulated fp32 (CUBLAS_EMULATE_SINGLE_PRECISION=1) for the upstream linears"
+                      if FP32_GEMM == "bf16x9" else "cuBLAS SIMT SGEMM (allow_tf32 off)"),
     }
 
 
@@ -326,6 +363,15 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = cap_bytes / (cap_ms / max(cap_calls, 1) / 1000.0) / 1e9 if cap_ms > 0 else 0.0
+    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch
+    # (profiles/traffic.json, written from the .ncu-rep by tools/ncu_traffic.py); null for other shapes
+    traffic = None
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["wca_capture_attention"]
+        if rec["workload"] == args.workload and rec["batch"] == args.batch and rec["model"] == args.model:
+            traffic = float(rec["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        pass
     dtw_calls, dtw_ms = kernel_ms.get("wca_dtw_align", (0, 0.0))
     cells = float(np.mean([dtw_cells[i] for i in used]))
 
@@ -346,7 +392,7 @@ def main():
             "clocks": clocks.summary(), "clocks_e2e": clocks_e2e.summary(),
             "roofline": {"kernel": "wca_capture_attention (QK^T capture + median filter + softmax)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": cap_bytes,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": cap_bytes,
                          "avg_launch_ms": cap_ms / max(cap_calls, 1)},
             "cpu_baseline": cpu,
             "stages_ms_per_step": {k: v[1] / args.steps for k, v in sorted(kernel_ms.items())},

@@ -2,6 +2,16 @@ import json
 import os
 import sys
 
+
+# WCA_FP32_GEMM=bf16x9 runs the GPU suite with the upstream linears on cuBLAS 12.9's BF16x9-emulated
+# fp32 GEMMs (what bench.py uses by default); the libraries must be mapped before torch is imported.
+if os.environ.get("WCA_FP32_GEMM") == "bf16x9":
+    import ctypes
+
+    os.environ.setdefault("CUBLAS_EMULATE_SINGLE_PRECISION", "1")
+    for _name in ("libcublasLt.so.12", "libcublas.so.12"):
+        ctypes.CDLL(os.path.join(os.environ.get("WCA_CUBLAS_DIR", "/usr/local/cuda/lib64"), _name), mode=ctypes.RTLD_GLOBAL)
+
 import numpy as np
 import pytest
 
