@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define WCA_ABI_VERSION 2
+#define WCA_ABI_VERSION 3
 #define WCA_MAX_LAYERS 64      /* large-v3 has 32 */
 #define WCA_MAX_MEDFILT 31     /* odd widths 1..31 */
 #define WCA_TOKENS_PER_SECOND 50.0 /* whisper.audio.TOKENS_PER_SECOND, timing.py:10,111 */
@@ -98,6 +98,24 @@ WCA_API int wca_capture_attention(const float *const *h_q_layers, const float *c
 /* Debug only: copies the timeline recorded by the last WCA_CAPTURE_TRACE launch (synchronises
  * the device).  Returns the number of int64 entries written (tiles x events) or a status < 0. */
 WCA_API int wca_debug_capture_trace(long long *h_out, int capacity);
+
+/* (1b) Encoder self-attention of the teacher-forced forward (timing.py:57-58 `model(mel, tokens)`;
+ * upstream whisper/model.py MultiHeadAttention.qkv_attention as used by AudioEncoder, where
+ * n_ctx = 1500): out = softmax(q k^T * Dh^-1/2) v per (batch, head), no mask, fp32 in and out,
+ * fp32-grade arithmetic on the tensor cores (3 x tf32 error-compensated products for both
+ * contractions).  d_q / d_k / d_v / d_out are row-major matrices of n_batch * n_ctx rows; row
+ * (b * n_ctx + t) holds position t of batch item b, columns [h*Dh, (h+1)*Dh) belong to head h;
+ * ld_* are the leading dimensions in floats (multiples of 4, pointers 16-byte aligned).
+ * The cross-attention maps themselves are NOT produced here (that is wca_capture_attention);
+ * this entry point only removes the fp32 CUDA-core attention from the encoder. */
+WCA_API int wca_encoder_attention(const float *d_q, const float *d_k, const float *d_v, float *d_out, int n_batch,
+                          int n_ctx, int n_heads, int head_dim, int64_t ld_q, int64_t ld_k, int64_t ld_v,
+                          int64_t ld_out, wca_stream_t stream);
+
+/* Debug only: while a non-null device buffer of >= 16640 floats is registered, CTA (0,0,0) of
+ * wca_encoder_attention dumps its first logit block, its un-normalised output rows and the
+ * softmax statistics there (tools/debug_enc_attn.py).  Pass NULL to stop. */
+WCA_API void wca_debug_enc_attn_buffer(float *d_buf);
 
 /* (2) Median filter -> *qk_scale -> softmax over already materialised logits.
  * Replaces timing.py:64-66 (`weights[..., :max_frames]`, whisper.timing.median_filter,

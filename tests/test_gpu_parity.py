@@ -324,3 +324,84 @@ def test_default_find_alignment_against_reference_fixture(name, timing, tokenize
     torch.testing.assert_close(weights.cpu(), torch.from_numpy(g["weights"]), rtol=2e-3, atol=2e-4)
     np.testing.assert_array_equal(np.round(st * 50).astype(int), np.round(g["start_times"] * 50).astype(int))
     np.testing.assert_array_equal(np.round(en * 50).astype(int), np.round(g["end_times"] * 50).astype(int))
+
+
+# ------------------------------------------------------------------------ encoder self-attention (row a2)
+def _attention_fp64(q, k, v, heads):
+    B, S, W = q.shape
+    sp = lambda t: t.double().view(B, S, heads, 64).transpose(1, 2)  # noqa: E731
+    o = torch.softmax(sp(q) @ sp(k).transpose(-1, -2) / 8.0, dim=-1) @ sp(v)
+    return o.transpose(1, 2).reshape(B, S, W)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (1, 63, 1), (1, 64, 2), (2, 129, 3), (2, 256, 2), (1, 512, 4),
+                                   (2, 1500, 2), (1, 1500, 16)], ids=str)
+def test_encoder_attention_matches_fp64_reference(shape, dev):
+    """wca_encoder_attention (tcgen05, 3 x tf32) against torch fp64 on the same inputs: fp32-grade,
+    i.e. no worse than a few times torch's own fp32 attention.  Covers one-key, ragged last key
+    block (63, 129, 1500 = 23*64 + 28), ragged last query block and a strided (fused qkv) input."""
+    from whisper_char_alignment_b200 import _cabi
+
+    B, S, H = shape
+    g = torch.Generator(device=dev).manual_seed(S * 131 + H)
+    fused = torch.randn(B, S, 3 * H * 64, device=dev, generator=g)
+    q, k, v = fused[..., : H * 64], fused[..., H * 64: 2 * H * 64], fused[..., 2 * H * 64:]
+    out = _cabi.encoder_attention(q, k, v, H)
+    ref = _attention_fp64(q, k, v, H)
+    err = (out.double() - ref).abs().max().item()
+    assert err <= 2e-6 * max(1.0, ref.abs().max().item()), err
+
+
+def test_encoder_attention_large_logits_and_lazy_rescale(dev):
+    """Peaky rows (|logit| ~ 100) and rows whose logits grow monotonically with the key index:
+    the second forces the lazy rescale of the running reference on every few blocks."""
+    from whisper_char_alignment_b200 import _cabi
+
+    g = torch.Generator(device=dev).manual_seed(5)
+    q, k, v = (torch.randn(1, 1500, 128, device=dev, generator=g) for _ in range(3))
+    out = _cabi.encoder_attention(q * 12.0, k, v, 2)
+    ref = _attention_fp64(q * 12.0, k, v, 2)
+    assert (out.double() - ref).abs().max().item() <= 3e-5  # |ref| ~ 4; torch fp32 itself is at 1.4e-5 here
+    q1 = torch.ones(1, 1500, 64, device=dev)
+    k1 = (torch.arange(1500, device=dev).float()[None, :, None] / 8.0).expand(1, 1500, 64).contiguous()
+    out = _cabi.encoder_attention(q1, k1, v[..., :64].contiguous(), 1)
+    ref = _attention_fp64(q1, k1, v[..., :64], 1)
+    assert (out.double() - ref).abs().max().item() <= 1e-5
+
+
+def test_encoder_attention_properties_at_full_size(dev):
+    """Size-independent properties at the medium shape (16 x 1500 x 16 heads): a constant V comes
+    back unchanged (rows of P sum to one), and permuting keys together with values changes nothing
+    beyond fp32 rounding."""
+    from whisper_char_alignment_b200 import _cabi
+
+    g = torch.Generator(device=dev).manual_seed(9)
+    B, S, H = 16, 1500, 16
+    q, k = (torch.randn(B, S, H * 64, device=dev, generator=g) for _ in range(2))
+    const_v = torch.randn(B, 1, H * 64, device=dev, generator=g).expand(B, S, H * 64).contiguous()
+    out = _cabi.encoder_attention(q, k, const_v, H)
+    torch.testing.assert_close(out, const_v, rtol=2e-6, atol=2e-6)
+    v = torch.randn(B, S, H * 64, device=dev, generator=g)
+    perm = torch.randperm(S, device=dev, generator=g)
+    a = _cabi.encoder_attention(q, k, v, H)
+    b = _cabi.encoder_attention(q, k[:, perm].contiguous(), v[:, perm].contiguous(), H)
+    torch.testing.assert_close(a, b, rtol=0, atol=2e-6)
+
+
+def test_model_forward_is_the_same_with_either_encoder_attention(oracle_models, dev):
+    """The product model with the tcgen05 encoder attention vs the same model on torch SDPA."""
+    from whisper_char_alignment_b200 import whisper_model
+
+    model = product_model(oracle_models("mini"), dev)
+    g = torch.Generator(device=dev).manual_seed(3)
+    mel = torch.randn(2, 80, 2 * model.dims.n_audio_ctx, device=dev, generator=g) * 0.3
+    keep = whisper_model.ENCODER_ATTENTION
+    try:
+        with torch.no_grad():
+            whisper_model.ENCODER_ATTENTION = "wca"
+            xa = model.encoder(mel)
+            whisper_model.ENCODER_ATTENTION = "sdpa"
+            xb = model.encoder(mel)
+    finally:
+        whisper_model.ENCODER_ATTENTION = keep
+    torch.testing.assert_close(xa, xb, rtol=1e-4, atol=2e-5)

@@ -97,7 +97,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert sorted(_cabi.EXPORTS) == names
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.wca_abi_version() == _cabi.ABI_VERSION == 2
+    assert lib.wca_abi_version() == _cabi.ABI_VERSION == 3
     assert lib.wca_dtw_workspace_bytes(4, 445, 1500) == 0  # largest legal Whisper problem fits in smem
     assert lib.wca_dtw_workspace_bytes(2, 1000, 4000) > 0
 

@@ -1,6 +1,8 @@
 """Where does a step go?  torch.profiler kernel table of one batched get_attentions + force_align."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _preload  # noqa: F401
 import torch
 from torch.profiler import ProfilerActivity, profile
 from whisper_char_alignment_b200 import synthetic, timing, whisper_model
@@ -25,7 +27,7 @@ for _ in range(2): step()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step(); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=90))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90))
 import time
 for fn, label in [(lambda: model.encoder(mels), "encoder"), ]:
     torch.cuda.synchronize(); t=time.perf_counter()

@@ -20,10 +20,10 @@ WCA_CAPTURE_RAW_LOGITS = 1
 WCA_CAPTURE_FORCE_SIMT = 2
 WCA_CAPTURE_TRACE = 4
 WCA_MAX_LAYERS = 64
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTS = (
-    "wca_abi_version", "wca_last_error", "wca_launch_count", "wca_device_info", "wca_capture_attention", "wca_debug_capture_trace", "wca_medfilt_softmax",
+    "wca_abi_version", "wca_last_error", "wca_launch_count", "wca_device_info", "wca_capture_attention", "wca_encoder_attention", "wca_debug_enc_attn_buffer", "wca_debug_capture_trace", "wca_medfilt_softmax",
     "wca_head_scores", "wca_topk_heads", "wca_aggregate_heads", "wca_dtw_workspace_bytes", "wca_dtw_align",
 )
 
@@ -73,6 +73,7 @@ def load() -> ctypes.CDLL:
     lib.wca_device_info.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(i32)]
     lib.wca_capture_attention.argtypes = [vp, vp, i32, i32, i32, i64, i64, i64, i64, vp, i32, i32, i32, i32, f32, vp,
                                           ctypes.c_uint, vp]
+    lib.wca_encoder_attention.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, vp]
     lib.wca_medfilt_softmax.argtypes = [vp, i64, i64, i32, i32, f32, vp, vp]
     lib.wca_head_scores.argtypes = [vp, vp, i32, i32, i32, i32, f32, f32, f32, vp, vp]
     lib.wca_topk_heads.argtypes = [vp, vp, i32, i32, vp, vp, vp]
@@ -213,6 +214,27 @@ def capture_attention(q_layers: Sequence[torch.Tensor], k_layers: Sequence[torch
                                          _dev_ptr(ws, torch.float32, "ws"), flags, _stream()),
             "wca_capture_attention",
         )
+
+
+def encoder_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_heads: int, out: torch.Tensor | None = None):
+    """q, k, v: (batch, n_ctx, n_heads*64) fp32, last dim contiguous, rows evenly strided.
+    Returns softmax(q k^T / 8) v in the same layout (wca_encoder_attention)."""
+    batch, n_ctx, width = q.shape
+    for t, name in ((q, "q"), (k, "k"), (v, "v")):
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise WcaError(f"encoder_attention: {name} must be an fp32 CUDA tensor (no CPU fallback exists)")
+        if t.shape != q.shape or t.stride(2) != 1 or t.stride(0) != n_ctx * t.stride(1):
+            raise WcaError(f"encoder_attention: {name} must be (batch, n_ctx, width) with contiguous rows")
+    if out is None:
+        out = torch.empty(batch, n_ctx, width, dtype=torch.float32, device=q.device)
+    with _timed("wca_encoder_attention"):
+        _check(
+            load().wca_encoder_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), _dev_ptr(out, torch.float32, "out"),
+                                         batch, n_ctx, n_heads, width // n_heads, q.stride(1), k.stride(1), v.stride(1),
+                                         out.stride(1), _stream()),
+            "wca_encoder_attention",
+        )
+    return out
 
 
 def medfilt_softmax(x: torch.Tensor, n_rows: int, ld_in: int, n_frames: int, medfilt_width: int, qk_scale: float,

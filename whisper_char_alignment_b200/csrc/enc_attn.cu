@@ -1,0 +1,472 @@
+// tcgen05 / TMEM / TMA non-causal attention for the Whisper audio encoder, fp32 in / fp32-grade out.
+//
+// Row a2 of the scope table (the teacher-forced forward, reference timing.py:57-58): the
+// reference runs the encoder's 1500 x 1500 self-attention in fp32 (upstream
+// MultiHeadAttention.qkv_attention; SDPA's fp32 path is a CUDA-core kernel and is a third of a
+// step once the linears run on the tensor cores).  This kernel keeps fp32 accuracy on the
+// tensor pipe with the same error-compensated split the capture kernel uses:
+//     x = hi + lo  (hi, lo rounded to tf32, x - hi exact),   a.b ~= lo.hi + hi.lo + hi.hi
+// for BOTH contractions (Q K^T and P V), 3 x tcgen05.mma.kind::tf32 each.
+//
+// One CTA = 128 queries of one (batch, head); keys are swept in blocks of 64.
+//   TMEM (512 columns)  Q_hi | Q_lo | S0 | S1 | P_lo0 | P_lo1 | T0 | T1    (64 columns each)
+//                       Q and P are A operands read straight from tensor memory (tcgen05.mma
+//                       with [a_tmem]); P_hi overwrites S in place.  T_b = P_j V_j of ONE key block
+//                       (24 MMAs); the blocks are summed in fp32 registers with round-to-nearest,
+//                       because the tensor core truncates when it accumulates: a 576-MMA chain into
+//                       one accumulator drifts by ~1e-5 relative, a 24-MMA chain by ~1e-6.
+//   shared memory       3-stage ring of {K_hi, V_hi, K_lo, V_lo} (16 KB each).  TMA lands K and V
+//                       with the 128-byte swizzle; that IS the UMMA canonical layout (K-major for
+//                       K in Q K^T, MN-major for V in P V), so the split is done in place with a
+//                       linear sweep: hi overwrites the tile, lo goes to a twin tile.
+//   softmax             one thread per query row (it also owns that row of O: 64 registers), online
+//                       with a LAZY rescale: the running reference m only moves when a block maximum
+//                       exceeds it by more than 2^32 (exp arguments stay far inside the fp32 range),
+//                       so O and l are rescaled only in that rare case.
+// Roles (10 warps): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 operand splitters
+// (also split Q into TMEM), warps 6-9 softmax / epilogue (thread <-> TMEM lane <-> query row;
+// a warp reaches TMEM lanes 32 * (warp % 4) .. + 31).
+#include <cuda.h>
+
+#include <cstring>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace wca {
+namespace ea {
+
+using namespace tc;
+
+constexpr int kThreads = 320;
+constexpr int kQRows = 128;                    // UMMA M
+constexpr int kKeys = 64;                      // keys per block: UMMA N of Q K^T, K extent of P V
+constexpr int kStages = 3;
+constexpr int kBoxCols = 32;                   // floats per TMA box row = 128 B = swizzle span
+constexpr int kQBoxBytes = kQRows * 128;       // 16384
+constexpr int kQBytes = 2 * kQBoxBytes;        // two column halves
+constexpr int kKvBoxBytes = kKeys * 128;       // 8192
+constexpr int kOpBytes = 2 * kKvBoxBytes;      // one operand part (K or V, hi or lo): 16384
+constexpr int kRawBytes = 2 * kOpBytes;        // what TMA writes per stage: K then V
+constexpr int kStageBytes = 2 * kRawBytes;     // + the lo twins
+constexpr int kOffQ = 0;
+constexpr int kOffStage = kOffQ + kQBytes;
+constexpr int kOffBar = kOffStage + kStages * kStageBytes;
+enum Bar {
+    kQFull = 0,
+    kQReady = 1,
+    kKvFull = 2,
+    kKvSplit = kKvFull + kStages,
+    kKvEmpty = kKvSplit + kStages,
+    kSFull = kKvEmpty + kStages,
+    kPReady = kSFull + 2,
+    kPvDone = kPReady + 2,
+    kNumBars = kPvDone + 2
+};
+constexpr int kOffTmem = kOffBar + kNumBars * 8;
+constexpr int kSmemBytes = kOffTmem + 16;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
+constexpr uint32_t kColQHi = 0, kColQLo = 64, kColS = 128, kColPLo = 256, kColT = 384, kTmemCols = 512;
+constexpr float kRescaleGap = 32.f;  // log2 units
+
+__device__ __forceinline__ void tma_load_box3(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+// 128-byte-swizzled operand descriptor, sm_100 version bit 46.  Layout type (bits 61-63):
+// 2 = SWIZZLE_128B (16-byte chunks XOR row & 7; what K-major tf32 operands use),
+// 1 = SWIZZLE_128B_BASE32B (32-byte chunks XOR row & 3; the ONLY swizzle MN-major tf32 operands
+//     accept -- TMA produces it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+constexpr uint64_t kSw128 = 2, kSw128Base32 = 1;
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr, uint32_t lbo, uint32_t sbo, uint64_t layout = kSw128) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (layout << 61);
+}
+// D[tmem] (+)= A[tmem] * B[smem]: A is read from tensor memory (lane = row, one tf32 per column).
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+struct Maps {
+    // 3-D (H*64, n_ctx, batch) fp32; boxes 32 x 128 x 1 (q), 32 x 64 x 1 (k, v); q and k with the
+    // 128-byte swizzle, v with the 128-byte swizzle on 32-byte atoms (MN-major tf32 operand)
+    CUtensorMap q, k, v;
+};
+struct Args {
+    float *out;
+    int64_t ld_out;
+    int n_ctx;
+    float scale_log2;  // Dh^-1/2 * log2(e)
+    float *dbg;        // debug only (wca_debug_enc_attn_buffer): CTA (0,0,0) dumps S of block 0, raw O, l, m
+};
+
+__global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Args a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.x * kQRows, head = blockIdx.y, batch = blockIdx.z;
+    const int col0 = head * kHeadDim;
+    const int n_blocks = (a.n_ctx + kKeys - 1) / kKeys;
+    const uint32_t bars = smem_u32(smem + kOffBar);
+    auto bar = [&](int which) { return bars + 8u * (uint32_t)which; };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kOffTmem);
+
+    if (tid == 0) {
+        mbar_init(bar(kQFull), 1);
+        mbar_init(bar(kQReady), 128);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(bar(kKvFull + i), 1);
+            mbar_init(bar(kKvSplit + i), 128);
+            mbar_init(bar(kKvEmpty + i), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar(kSFull + i), 1);
+            mbar_init(bar(kPReady + i), 128);
+            mbar_init(bar(kPvDone + i), 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            tma_prefetch_map(&maps.q);
+            tma_prefetch_map(&maps.k);
+            tma_prefetch_map(&maps.v);
+            mbar_expect_tx(bar(kQFull), kQBytes);
+            tma_load_box3(smem_u32(smem + kOffQ), &maps.q, col0, q0, batch, bar(kQFull));
+            tma_load_box3(smem_u32(smem + kOffQ) + kQBoxBytes, &maps.q, col0 + kBoxCols, q0, batch, bar(kQFull));
+            for (int j = 0; j < n_blocks; ++j) {
+                const int s = j % kStages;
+                mbar_wait(bar(kKvEmpty + s), ((j / kStages) & 1) ^ 1);  // first lap passes immediately
+                const uint32_t dst = smem_u32(smem + kOffStage + s * kStageBytes);
+                mbar_expect_tx(bar(kKvFull + s), kRawBytes);  // rows past n_ctx are zero-filled, boxes are always full
+                tma_load_box3(dst, &maps.k, col0, j * kKeys, batch, bar(kKvFull + s));
+                tma_load_box3(dst + kKvBoxBytes, &maps.k, col0 + kBoxCols, j * kKeys, batch, bar(kKvFull + s));
+                tma_load_box3(dst + kOpBytes, &maps.v, col0, j * kKeys, batch, bar(kKvFull + s));
+                tma_load_box3(dst + kOpBytes + kKvBoxBytes, &maps.v, col0 + kBoxCols, j * kKeys, batch, bar(kKvFull + s));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer (warp-uniform control flow, one elected lane issues) =================
+        const uint32_t idesc_qk = instr_desc_tf32(kQRows, kKeys);                 // A tmem (K-major), B K-major
+        const uint32_t idesc_pv = instr_desc_tf32(kQRows, kHeadDim) | (1u << 16);  // B = V, MN-major
+        mbar_wait(bar(kQReady), 0);
+        tc_fence_after();
+        for (int j = 0; j <= n_blocks; ++j) {
+            if (j < n_blocks) {
+                // ---- S[j & 1] = Q K_j^T
+                const int s = j % kStages;
+                mbar_wait(bar(kKvSplit + s), (j / kStages) & 1);
+                tc_fence_after();
+                const uint32_t k_hi = smem_u32(smem + kOffStage + s * kStageBytes);
+                const uint32_t k_lo = k_hi + kRawBytes;
+                const uint32_t d = tmem + kColS + (uint32_t)(j & 1) * kKeys;
+                if (elect_one()) {
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {  // small terms first: lo.hi, hi.lo, hi.hi
+                        const uint32_t a_col = tmem + (pass == 0 ? kColQLo : kColQHi);
+                        const uint32_t b_base = pass == 1 ? k_lo : k_hi;
+#pragma unroll
+                        for (int ks = 0; ks < kHeadDim / 8; ++ks) {
+                            // K-major, 128B swizzle: 8 tf32 = 32 bytes along the row; second column half is the next box
+                            const uint64_t db = smem_desc_sw128(b_base + (ks >> 2) * kKvBoxBytes + (ks & 3) * 32, 16, 1024);
+                            umma_tf32_ts(d, a_col + (uint32_t)(ks * 8), db, idesc_qk, (pass | ks) != 0);
+                        }
+                    }
+                    umma_commit(bar(kSFull + (j & 1)));
+                }
+                __syncwarp();
+            }
+            if (j >= 1) {
+                // ---- O += P_{j-1} V_{j-1}
+                const int i = j - 1, s = i % kStages, b = i & 1;
+                mbar_wait(bar(kPReady + b), (i >> 1) & 1);
+                tc_fence_after();
+                const uint32_t v_hi = smem_u32(smem + kOffStage + s * kStageBytes) + kOpBytes;
+                const uint32_t v_lo = v_hi + kRawBytes;
+                const uint32_t p_hi = tmem + kColS + (uint32_t)b * kKeys, p_lo = tmem + kColPLo + (uint32_t)b * kKeys;
+                if (elect_one()) {
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t a_col = pass == 0 ? p_lo : p_hi;
+                        const uint32_t b_base = pass == 1 ? v_lo : v_hi;
+#pragma unroll
+                        for (int ks = 0; ks < kKeys / 8; ++ks) {
+                            // MN-major, 128B swizzle with 32B atoms: 4 keys x 128 B per atom, so the 8 keys of one
+                            // MMA are two atoms SBO = 512 B apart; the two 32-float halves of d are LBO apart
+                            const uint64_t db = smem_desc_sw128(b_base + ks * 1024, kKvBoxBytes, 512, kSw128Base32);
+                            umma_tf32_ts(tmem + kColT + (uint32_t)b * kHeadDim, a_col + (uint32_t)(ks * 8), db, idesc_pv,
+                                         (pass | ks) != 0);
+                        }
+                    }
+                    umma_commit(bar(kKvEmpty + s));
+                    umma_commit(bar(kPvDone + b));
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 2 && warp < 6) {
+        // ================= operand splitters =================
+        const int t = tid - 64;                    // linear index for the in-place K / V sweep
+        const int qrow = (warp & 3) * 32 + lane;   // query row this thread splits (its TMEM lane)
+        {
+            mbar_wait(bar(kQFull), 0);
+            const unsigned char *qs = smem + kOffQ;
+            const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll
+            for (int c16 = 0; c16 < 4; ++c16) {  // 16 columns at a time
+                float hi[16], lo[16];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const int ch = c16 * 4 + q4;  // 16-byte chunk of the 256-byte row
+                    const float4 v = *reinterpret_cast<const float4 *>(qs + (ch >> 3) * kQBoxBytes + qrow * 128 +
+                                                                       (((ch & 7) ^ (qrow & 7)) << 4));
+                    const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        hi[q4 * 4 + e] = rna_tf32(x[e]);
+                        lo[q4 * 4 + e] = rna_tf32(x[e] - hi[q4 * 4 + e]);
+                    }
+                }
+                tmem_st16(trow + kColQHi + (uint32_t)(c16 * 16), hi);
+                tmem_st16(trow + kColQLo + (uint32_t)(c16 * 16), lo);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar(kQReady));
+        }
+        for (int j = 0; j < n_blocks; ++j) {
+            const int s = j % kStages;
+            mbar_wait(bar(kKvFull + s), (j / kStages) & 1);
+            float4 *raw = reinterpret_cast<float4 *>(smem + kOffStage + s * kStageBytes);
+            float4 *twin = reinterpret_cast<float4 *>(smem + kOffStage + s * kStageBytes + kRawBytes);
+            constexpr int kIters = kRawBytes / 16 / 128;  // 16 float4 per thread
+#pragma unroll 4
+            for (int it = 0; it < kIters; ++it) {
+                const int idx = it * 128 + t;
+                const float4 v = raw[idx];
+                float4 h, l;
+                h.x = rna_tf32(v.x), h.y = rna_tf32(v.y), h.z = rna_tf32(v.z), h.w = rna_tf32(v.w);
+                l.x = rna_tf32(v.x - h.x), l.y = rna_tf32(v.y - h.y), l.z = rna_tf32(v.z - h.z), l.w = rna_tf32(v.w - h.w);
+                raw[idx] = h;
+                twin[idx] = l;
+            }
+            fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+            mbar_arrive(bar(kKvSplit + s));
+        }
+    } else if (warp >= 6) {
+        // ================= softmax + epilogue: thread <-> query row =================
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const float c = a.scale_log2;
+        float m_ref = 0.f, l_sum = 0.f;
+        float acc[4][16];  // this row of O, summed over key blocks in fp32 (round-to-nearest)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[q][e] = 0.f;
+        int folded = 0;  // key blocks whose P V partial has been added into acc
+        // acc += T[i & 1] once P_i V_i has landed
+        auto fold = [&](int i) {
+            mbar_wait(bar(kPvDone + (i & 1)), (i >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float t[16];
+                tmem_ld16_issue(trow + kColT + (uint32_t)((i & 1) * kHeadDim + q * 16), t);
+                tmem_ld_wait(t);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acc[q][e] += t[e];
+            }
+        };
+        for (int j = 0; j < n_blocks; ++j) {
+            const int b = j & 1;
+            mbar_wait(bar(kSFull + b), (j >> 1) & 1);
+            tc_fence_after();
+            const uint32_t s_col = trow + kColS + (uint32_t)b * kKeys;
+            float sv[4][16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tmem_ld16_issue(s_col + (uint32_t)(q * 16), sv[q]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tmem_ld_wait(sv[q]);
+            if (a.dbg && j == 0 && blockIdx.x + blockIdx.y + blockIdx.z == 0)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) a.dbg[row * 64 + q * 16 + e] = sv[q][e];
+            const int n_valid = min(kKeys, a.n_ctx - j * kKeys);  // < 64 only for the last block
+            float bm = -INFINITY;
+            if (n_valid == kKeys) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) bm = fmaxf(bm, sv[q][e]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (q * 16 + e < n_valid) bm = fmaxf(bm, sv[q][e]);
+            }
+            bm *= c;
+            if (j == 0) {
+                m_ref = bm;
+            } else {
+                const bool need = bm > m_ref + kRescaleGap;
+                if (__any_sync(0xffffffffu, need)) {
+                    // rare: move the reference.  Everything accumulated so far (including the partial of
+                    // block j-1, which was computed against the old reference) is rescaled in registers.
+                    if (folded < j) {
+                        fold(j - 1);
+                        folded = j;
+                    }
+                    const float nm = need ? bm : m_ref;
+                    const float f = ex2_approx(m_ref - nm);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) acc[q][e] *= f;
+                    l_sum *= f;
+                    m_ref = nm;
+                }
+            }
+            // P_lo[b] and T[b] are free: P V of block j-2 completed before it was folded (iteration j-1)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float hi[16], lo[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    float p = ex2_approx(fmaf(sv[q][e], c, -m_ref));
+                    if (q * 16 + e >= n_valid) p = 0.f;
+                    l_sum += p;
+                    hi[e] = rna_tf32(p);
+                    lo[e] = rna_tf32(p - hi[e]);
+                }
+                tmem_st16(s_col + (uint32_t)(q * 16), hi);
+                tmem_st16(trow + kColPLo + (uint32_t)(b * kKeys + q * 16), lo);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar(kPReady + b));
+            if (j >= 1 && folded < j) {  // off the critical path: the tensor pipe is busy with Q K_{j+1}^T
+                fold(j - 1);
+                folded = j;
+            }
+        }
+        fold(n_blocks - 1);
+        // ---- epilogue: O / l -> global
+        const float inv = 1.f / l_sum;
+        const bool row_ok = q0 + row < a.n_ctx;
+        float *dst = a.out + ((int64_t)batch * a.n_ctx + q0 + row) * a.ld_out + col0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (a.dbg && blockIdx.x + blockIdx.y + blockIdx.z == 0) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) a.dbg[8192 + row * 64 + q * 16 + e] = acc[q][e];
+                a.dbg[16384 + row] = l_sum;
+                a.dbg[16512 + row] = m_ref;
+            }
+            if (row_ok) {
+#pragma unroll
+                for (int e = 0; e < 16; e += 4)
+                    *reinterpret_cast<float4 *>(dst + q * 16 + e) =
+                        make_float4(acc[q][e] * inv, acc[q][e + 1] * inv, acc[q][e + 2] * inv, acc[q][e + 3] * inv);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, kTmemCols);
+    }
+}
+
+}  // namespace ea
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_map3(EncodeTiledFn encode, CUtensorMap *map, const float *base, int64_t cols, int64_t n_ctx, int64_t batch,
+                       int64_t ld, int box_rows, CUtensorMapSwizzle swizzle) {
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)n_ctx, (cuuint64_t)batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), (cuuint64_t)n_ctx * (cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)ea::kBoxCols, (cuuint32_t)box_rows, 1};
+    const cuuint32_t elem[3] = {1, 1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, elem,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d (cols %lld, n_ctx %lld, batch %lld, ld %lld)", (int)r,
+                  (long long)cols, (long long)n_ctx, (long long)batch, (long long)ld);
+        return WCA_ERR_CUDA;
+    }
+    return WCA_OK;
+}
+
+static float *g_enc_attn_dbg = nullptr;
+void set_enc_attn_debug_buffer(float *d_buf) { g_enc_attn_dbg = d_buf; }
+
+int launch_encoder_attention(const float *d_q, const float *d_k, const float *d_v, float *d_out, int n_batch, int n_ctx,
+                             int n_heads, int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_out, cudaStream_t stream) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        WCA_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) {
+            set_error("encoder_attention: the driver does not export cuTensorMapEncodeTiled");
+            return WCA_ERR_CUDA;
+        }
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    ea::Maps maps;
+    memset(&maps, 0, sizeof(maps));
+    const int64_t cols = (int64_t)n_heads * kHeadDim;
+    int rc = encode_map3(encode, &maps.q, d_q, cols, n_ctx, n_batch, ld_q, ea::kQRows, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = encode_map3(encode, &maps.k, d_k, cols, n_ctx, n_batch, ld_k, ea::kKeys, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = encode_map3(encode, &maps.v, d_v, cols, n_ctx, n_batch, ld_v, ea::kKeys, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    ea::Args a;
+    a.out = d_out;
+    a.ld_out = ld_out;
+    a.n_ctx = n_ctx;
+    a.dbg = g_enc_attn_dbg;
+    a.scale_log2 = (float)(0.125 * 1.4426950408889634);  // Dh^-1/2 (= (Dh^-1/4)^2 of upstream) * log2(e)
+    WCA_CUDA(cudaFuncSetAttribute(ea::enc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ea::kSmemBytes));
+    const dim3 grid((unsigned)((n_ctx + ea::kQRows - 1) / ea::kQRows), (unsigned)n_heads, (unsigned)n_batch);
+    ea::enc_attn_kernel<<<grid, ea::kThreads, ea::kSmemBytes, stream>>>(maps, a);
+    WCA_LAUNCH_CHECK("enc_attn_kernel");
+    return WCA_OK;
+}
+
+}  // namespace wca

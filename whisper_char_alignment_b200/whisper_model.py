@@ -19,6 +19,7 @@ Differences from the upstream module that matter for this path:
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import asdict, dataclass
 
 import torch
@@ -54,6 +55,11 @@ def dims_for(name: str) -> ModelDimensions:
     return ModelDimensions(*SIZES[name])
 
 
+#: "wca": the encoder's non-causal self-attention runs on csrc/enc_attn.cu; "sdpa": torch SDPA (fp32 CUDA-core
+#: kernel).  Decoder self/cross attention (a few dozen tokens) always stays on SDPA.
+ENCODER_ATTENTION = os.environ.get("WCA_ENCODER_ATTENTION", "wca")
+
+
 class _Norm(nn.LayerNorm):
     def forward(self, x):
         return super().forward(x.float()).to(x.dtype)
@@ -87,7 +93,15 @@ class Attention(nn.Module):
 
     def forward(self, x, xa=None, causal: bool = False):
         src = x if xa is None else xa
-        q, k, v = self._split(self.query(x)), self._split(self.key(src)), self._split(self.value(src))
+        q, k, v = self.query(x), self.key(src), self.value(src)
+        if (xa is None and not causal and ENCODER_ATTENTION == "wca" and q.is_cuda and q.dtype == torch.float32
+                and q.shape[-1] == 64 * self.n_head):
+            # encoder self-attention: the sm_100a tcgen05 kernel (csrc/enc_attn.cu) reads the projection
+            # outputs in place (no head split / transposes) and keeps fp32 accuracy with 3 x tf32 products
+            from . import _cabi
+
+            return self.out(_cabi.encoder_attention(q, k, v, self.n_head)), None
+        q, k, v = self._split(q), self._split(k), self._split(v)
         # SDPA's default scale is d_head^-1/2 == (d_head^-1/4)^2, the published scaling
         ctx = F.scaled_dot_product_attention(q, k, v, is_causal=causal and q.shape[2] > 1)
         return self.out(ctx.transpose(1, 2).flatten(2)), None
