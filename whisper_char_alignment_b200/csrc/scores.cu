@@ -131,6 +131,8 @@ __global__ void __launch_bounds__(256) aggregate_heads_kernel(const float *__res
             for (int t = warp; t < T; t += warps) acc_s[t * kWarp + lane] += a[(int64_t)t * F + f] / cn;
     }
 
+    // rows are accumulated by warp (t % warps) but written out by warp ((t - row_begin) % warps)
+    __syncthreads();
     const float count = (float)u.n_sel;  // torch.mean = sum / count
     if (live)
         for (int t = u.row_begin + warp; t < u.row_end; t += warps)
