@@ -112,7 +112,7 @@ WCA_API int wca_encoder_attention(const float *d_q, const float *d_k, const floa
                           int n_ctx, int n_heads, int head_dim, int64_t ld_q, int64_t ld_k, int64_t ld_v,
                           int64_t ld_out, wca_stream_t stream);
 
-/* Debug only: while a non-null device buffer of >= 16640 floats is registered, CTA (0,0,0) of
+/* Debug only: while a non-null device buffer of >= 20000 floats is registered, CTA (0,0,0) of
  * wca_encoder_attention dumps its first logit block, its un-normalised output rows and the
  * softmax statistics there (tools/debug_enc_attn.py).  Pass NULL to stop. */
 WCA_API void wca_debug_enc_attn_buffer(float *d_buf);

@@ -7,7 +7,7 @@ dev = torch.device("cuda:0")
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 lib = _cabi.load()
 lib.wca_debug_enc_attn_buffer.argtypes = [ctypes.c_void_p]
-dbg = torch.zeros(16640, device=dev)
+dbg = torch.zeros(20000, device=dev)
 lib.wca_debug_enc_attn_buffer(dbg.data_ptr())
 torch.manual_seed(0)
 q, k, v = (torch.randn(1, S, 64, device=dev) for _ in range(3))

@@ -5,7 +5,8 @@
 // MultiHeadAttention.qkv_attention; SDPA's fp32 path is a CUDA-core kernel and is a third of a
 // step once the linears run on the tensor cores).  This kernel keeps fp32 accuracy on the
 // tensor pipe with the same error-compensated split the capture kernel uses:
-//     x = hi + lo  (hi, lo rounded to tf32, x - hi exact),   a.b ~= lo.hi + hi.lo + hi.hi
+//     x = hi + lo  (hi = x chopped to tf32 by the tensor core itself, lo = x - hi exact),
+//     a.b ~= lo.hi + hi.lo + hi.hi
 // for BOTH contractions (Q K^T and P V), 3 x tcgen05.mma.kind::tf32 each.
 //
 // One CTA = 128 queries of one (batch, head); keys are swept in blocks of 64.
@@ -17,17 +18,21 @@
 //                       one accumulator drifts by ~1e-5 relative, a 24-MMA chain by ~1e-6.
 //   shared memory       3-stage ring of {K_hi, V_hi, K_lo, V_lo} (16 KB each).  TMA lands K and V
 //                       with the 128-byte swizzle; that IS the UMMA canonical layout (K-major for
-//                       K in Q K^T, MN-major for V in P V), so the split is done in place with a
-//                       linear sweep: hi overwrites the tile, lo goes to a twin tile.
-//   softmax             one thread per query row (it also owns that row of O: 64 registers), online
-//                       with a LAZY rescale: the running reference m only moves when a block maximum
-//                       exceeds it by more than 2^32 (exp arguments stay far inside the fp32 range),
-//                       so O and l are rescaled only in that rare case.
-// Roles (10 warps): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 operand splitters
-// (also split Q into TMEM), warps 6-9 softmax / epilogue (thread <-> TMEM lane <-> query row;
-// a warp reaches TMEM lanes 32 * (warp % 4) .. + 31).
+//                       K in Q K^T, MN-major for V in P V), so the split is a linear sweep that
+//                       leaves the tile alone (it is hi) and writes lo to a twin tile.
+//   softmax             one thread per query row, online with a LAZY rescale: the running reference m
+//                       only moves when a block maximum exceeds it by more than 2^32 (exp arguments
+//                       stay far inside the fp32 range), so a block is normally ONE streaming pass
+//                       (exp against the current reference and the block maximum together) and O / l
+//                       are rescaled only in that rare case (factor handed over through shared memory).
+// Roles (15 warps): warp 0 P V issuer, warp 1 Q K^T issuer (two warps on two schedulers: issuing one
+// 128x64x8 MMA costs about as many cycles as the tensor pipe needs to run it), warps 2-5 operand
+// splitters (also split Q into TMEM), warps 6-9 softmax, warps 10-13 accumulate (own the rows of O:
+// 64 registers) and epilogue, warp 14 TMA producer.  Thread <-> TMEM lane <-> query row; a warp
+// reaches TMEM lanes 32 * (warp % 4) .. + 31.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -38,7 +43,7 @@ namespace ea {
 
 using namespace tc;
 
-constexpr int kThreads = 320;
+constexpr int kThreads = 480;
 constexpr int kQRows = 128;                    // UMMA M
 constexpr int kKeys = 64;                      // keys per block: UMMA N of Q K^T, K extent of P V
 constexpr int kStages = 3;
@@ -51,7 +56,8 @@ constexpr int kRawBytes = 2 * kOpBytes;        // what TMA writes per stage: K t
 constexpr int kStageBytes = 2 * kRawBytes;     // + the lo twins
 constexpr int kOffQ = 0;
 constexpr int kOffStage = kOffQ + kQBytes;
-constexpr int kOffBar = kOffStage + kStages * kStageBytes;
+constexpr int kOffFactor = kOffStage + kStages * kStageBytes;   // [4][128] rescale factors + [128] row sums
+constexpr int kOffBar = kOffFactor + 5 * kQRows * 4;
 enum Bar {
     kQFull = 0,
     kQReady = 1,
@@ -60,8 +66,10 @@ enum Bar {
     kKvEmpty = kKvSplit + kStages,
     kSFull = kKvEmpty + kStages,
     kPReady = kSFull + 2,
-    kPvDone = kPReady + 2,
-    kNumBars = kPvDone + 2
+    kPvDone = kPReady + 2,   // count 1 (tcgen05.commit); waited by the softmax AND the accumulate warpgroup
+    kTFree = kPvDone + 2,    // accumulate warpgroup has read T[b]
+    kLReady = kTFree + 2,    // row sums published
+    kNumBars = kLReady + 1
 };
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
@@ -86,21 +94,43 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr, uint32_t lbo,
            ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (layout << 61);
 }
 // D[tmem] (+)= A[tmem] * B[smem]: A is read from tensor memory (lane = row, one tf32 per column).
+// Executed by the WHOLE warp with `elected` true in one lane: only the instruction is predicated, so
+// the descriptor arithmetic around it stays in convergent code and on the uniform datapath (with the
+// loop inside a divergent `if (elected)` every operand went through R2UR: ~45 cycles per MMA issued,
+// more than the 32 cycles a 128x64x8 tf32 MMA occupies the tensor pipe).
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                             uint32_t accumulate) {
+                                             uint32_t accumulate, uint32_t elected) {
     asm volatile(
         "{\n\t"
-        ".reg .pred p;\n\t"
+        ".reg .pred p, e;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "setp.ne.b32 e, %5, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
         "}" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(elected)
         : "memory");
 }
-__device__ __forceinline__ float rna_tf32(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+__device__ __forceinline__ void umma_commit_if(uint32_t bar, uint32_t elected) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e;\n\t"
+        "setp.ne.b32 e, %1, 0;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(bar),
+        "r"(elected)
+        : "memory");
+}
+// x = hi + lo for the 3 x tf32 product.  tcgen05.mma.kind::tf32 ignores the 13 low mantissa bits of
+// its operands (measured: with hi = x left as is and lo = x - chop(x) the results are fp32-grade; a
+// rounding tensor core would be off by a tf32 ulp), so hi needs no instruction and no store at all;
+// lo is exact in fp32 and is chopped to its 11 leading bits by the tensor core: |error| <= 2^-21 |x|.
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// debug timeline: CTA (0,0,0) stores the low 32 bits of clock64() per (event, key block) behind the dump area
+enum Ev { kEvTmaIssue = 0, kEvKvFull, kEvSplitDone, kEvQkIssue, kEvQkIssued, kEvSFull, kEvExpDone, kEvPArrive, kEvPReady,
+          kEvPvIssued, kEvPvDone, kEvFoldDone, kNumEv };
+__device__ __forceinline__ void stamp(float *dbg, bool on, int ev, int j) {
+    if (on && j < 32) reinterpret_cast<uint32_t *>(dbg)[17000 + ev * 32 + j] = (uint32_t)clock64();
 }
 
 struct Maps {
@@ -113,6 +143,7 @@ struct Args {
     int64_t ld_out;
     int n_ctx;
     float scale_log2;  // Dh^-1/2 * log2(e)
+    unsigned skip;     // debug only (env WCA_EA_SKIP): 2 P V MMAs, 4 Q K^T MMAs, 8 operand split
     float *dbg;        // debug only (wca_debug_enc_attn_buffer): CTA (0,0,0) dumps S of block 0, raw O, l, m
 };
 
@@ -125,6 +156,7 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
     const uint32_t bars = smem_u32(smem + kOffBar);
     auto bar = [&](int which) { return bars + 8u * (uint32_t)which; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kOffTmem);
+    const bool tr = a.dbg != nullptr && blockIdx.x + blockIdx.y + blockIdx.z == 0 && lane == 0 && (warp < 2 || (warp & 3) == 2);  // incl. warp 14
 
     if (tid == 0) {
         mbar_init(bar(kQFull), 1);
@@ -138,7 +170,9 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
             mbar_init(bar(kSFull + i), 1);
             mbar_init(bar(kPReady + i), 128);
             mbar_init(bar(kPvDone + i), 1);
+            mbar_init(bar(kTFree + i), 128);
         }
+        mbar_init(bar(kLReady), 128);
         fence_mbar_init();
     }
     if (warp == 0) {
@@ -150,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 14) {
         // ================= TMA producer =================
         if (lane == 0) {
             tma_prefetch_map(&maps.q);
@@ -162,6 +196,7 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
             for (int j = 0; j < n_blocks; ++j) {
                 const int s = j % kStages;
                 mbar_wait(bar(kKvEmpty + s), ((j / kStages) & 1) ^ 1);  // first lap passes immediately
+                stamp(a.dbg, tr, kEvTmaIssue, j);
                 const uint32_t dst = smem_u32(smem + kOffStage + s * kStageBytes);
                 mbar_expect_tx(bar(kKvFull + s), kRawBytes);  // rows past n_ctx are zero-filled, boxes are always full
                 tma_load_box3(dst, &maps.k, col0, j * kKeys, batch, bar(kKvFull + s));
@@ -172,63 +207,74 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ================= MMA issuer (warp-uniform control flow, one elected lane issues) =================
-        const uint32_t idesc_qk = instr_desc_tf32(kQRows, kKeys);                 // A tmem (K-major), B K-major
-        const uint32_t idesc_pv = instr_desc_tf32(kQRows, kHeadDim) | (1u << 16);  // B = V, MN-major
+        // ================= Q K^T issuer: the whole warp runs the loop, one elected lane issues =================
+        const uint32_t idesc_qk = instr_desc_tf32(kQRows, kKeys);  // A tmem (K-major), B K-major
+        const uint32_t elected = elect_one() ? 1u : 0u;
+        const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);  // warp-uniform for the compiler
+        const uint32_t stage0 = smem_u32(smem + kOffStage);
+        const uint32_t skip_qk = a.skip & 4;
         mbar_wait(bar(kQReady), 0);
-        tc_fence_after();
-        for (int j = 0; j <= n_blocks; ++j) {
-            if (j < n_blocks) {
-                // ---- S[j & 1] = Q K_j^T
-                const int s = j % kStages;
-                mbar_wait(bar(kKvSplit + s), (j / kStages) & 1);
-                tc_fence_after();
-                const uint32_t k_hi = smem_u32(smem + kOffStage + s * kStageBytes);
-                const uint32_t k_lo = k_hi + kRawBytes;
-                const uint32_t d = tmem + kColS + (uint32_t)(j & 1) * kKeys;
-                if (elect_one()) {
+        for (int j = 0; j < n_blocks; ++j) {
+            // ---- S[j & 1] = Q K_j^T
+            const int s = j % kStages, b = j & 1;
+            mbar_wait(bar(kKvSplit + s), (j / kStages) & 1);
+            if (j >= 2) mbar_wait(bar(kPvDone + b), ((j - 2) >> 1) & 1);  // P V of block j-2 no longer reads P_hi = S[b]
+            tc_fence_after();
+            stamp(a.dbg, tr, kEvQkIssue, j);
+            const uint32_t k_hi = stage0 + (uint32_t)s * kStageBytes;
+            const uint32_t d = tm + kColS + (uint32_t)b * kKeys;
+            // K-major, 128B swizzle, SBO = 1024 B between 8-key groups; 8 tf32 = 32 bytes along the row,
+            // the second column half is the next TMA box
+            const uint64_t dk_hi = smem_desc_sw128(k_hi, 16, 1024), dk_lo = smem_desc_sw128(k_hi + kRawBytes, 16, 1024);
+            if (!skip_qk) {
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {  // small terms first: lo.hi, hi.lo, hi.hi
-                        const uint32_t a_col = tmem + (pass == 0 ? kColQLo : kColQHi);
-                        const uint32_t b_base = pass == 1 ? k_lo : k_hi;
+                for (int pass = 0; pass < 3; ++pass) {  // small terms first: lo.hi, hi.lo, hi.hi
+                    const uint32_t a_col = tm + (pass == 0 ? kColQLo : kColQHi);
+                    const uint64_t db = pass == 1 ? dk_lo : dk_hi;
 #pragma unroll
-                        for (int ks = 0; ks < kHeadDim / 8; ++ks) {
-                            // K-major, 128B swizzle: 8 tf32 = 32 bytes along the row; second column half is the next box
-                            const uint64_t db = smem_desc_sw128(b_base + (ks >> 2) * kKvBoxBytes + (ks & 3) * 32, 16, 1024);
-                            umma_tf32_ts(d, a_col + (uint32_t)(ks * 8), db, idesc_qk, (pass | ks) != 0);
-                        }
-                    }
-                    umma_commit(bar(kSFull + (j & 1)));
+                    for (int ks = 0; ks < kHeadDim / 8; ++ks)
+                        umma_tf32_ts(d, a_col + (uint32_t)(ks * 8),
+                                     db + (uint64_t)(((ks >> 2) * kKvBoxBytes + (ks & 3) * 32) >> 4), idesc_qk,
+                                     (pass | ks) != 0, elected);
                 }
-                __syncwarp();
             }
-            if (j >= 1) {
-                // ---- O += P_{j-1} V_{j-1}
-                const int i = j - 1, s = i % kStages, b = i & 1;
-                mbar_wait(bar(kPReady + b), (i >> 1) & 1);
-                tc_fence_after();
-                const uint32_t v_hi = smem_u32(smem + kOffStage + s * kStageBytes) + kOpBytes;
-                const uint32_t v_lo = v_hi + kRawBytes;
-                const uint32_t p_hi = tmem + kColS + (uint32_t)b * kKeys, p_lo = tmem + kColPLo + (uint32_t)b * kKeys;
-                if (elect_one()) {
+            umma_commit_if(bar(kSFull + b), elected);
+            stamp(a.dbg, tr, kEvQkIssued, j);
+        }
+    } else if (warp == 0) {
+        // ================= P V issuer (its own warp, on another scheduler than the Q K^T issuer) =================
+        const uint32_t idesc_pv = instr_desc_tf32(kQRows, kHeadDim) | (1u << 16);  // B = V, MN-major
+        const uint32_t elected = elect_one() ? 1u : 0u;
+        const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+        const uint32_t stage0 = smem_u32(smem + kOffStage);
+        const uint32_t skip_pv = a.skip & 2;
+        for (int i = 0; i < n_blocks; ++i) {
+            // ---- T[i & 1] = P_i V_i
+            const int s = i % kStages, b = i & 1;
+            mbar_wait(bar(kPReady + b), (i >> 1) & 1);
+            if (i >= 2) mbar_wait(bar(kTFree + b), ((i - 2) >> 1) & 1);  // T[b] of block i-2 has been folded
+            tc_fence_after();
+            stamp(a.dbg, tr, kEvPReady, i);
+            const uint32_t v_hi = stage0 + (uint32_t)s * kStageBytes + kOpBytes;
+            const uint32_t p_hi = tm + kColS + (uint32_t)b * kKeys, p_lo = tm + kColPLo + (uint32_t)b * kKeys;
+            // MN-major, 128B swizzle with 32B atoms: 4 keys x 128 B per atom, so the 8 keys of one MMA are
+            // two atoms SBO = 512 B apart; the two 32-float halves of d are LBO apart
+            const uint64_t dv_hi = smem_desc_sw128(v_hi, kKvBoxBytes, 512, kSw128Base32);
+            const uint64_t dv_lo = smem_desc_sw128(v_hi + kRawBytes, kKvBoxBytes, 512, kSw128Base32);
+            if (!skip_pv) {
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t a_col = pass == 0 ? p_lo : p_hi;
-                        const uint32_t b_base = pass == 1 ? v_lo : v_hi;
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t a_col = pass == 0 ? p_lo : p_hi;
+                    const uint64_t db = pass == 1 ? dv_lo : dv_hi;
 #pragma unroll
-                        for (int ks = 0; ks < kKeys / 8; ++ks) {
-                            // MN-major, 128B swizzle with 32B atoms: 4 keys x 128 B per atom, so the 8 keys of one
-                            // MMA are two atoms SBO = 512 B apart; the two 32-float halves of d are LBO apart
-                            const uint64_t db = smem_desc_sw128(b_base + ks * 1024, kKvBoxBytes, 512, kSw128Base32);
-                            umma_tf32_ts(tmem + kColT + (uint32_t)b * kHeadDim, a_col + (uint32_t)(ks * 8), db, idesc_pv,
-                                         (pass | ks) != 0);
-                        }
-                    }
-                    umma_commit(bar(kKvEmpty + s));
-                    umma_commit(bar(kPvDone + b));
+                    for (int ks = 0; ks < kKeys / 8; ++ks)
+                        umma_tf32_ts(tm + kColT + (uint32_t)b * kHeadDim, a_col + (uint32_t)(ks * 8),
+                                     db + (uint64_t)((ks * 1024) >> 4), idesc_pv, (pass | ks) != 0, elected);
                 }
-                __syncwarp();
             }
+            umma_commit_if(bar(kKvEmpty + s), elected);
+            umma_commit_if(bar(kPvDone + b), elected);
+            stamp(a.dbg, tr, kEvPvIssued, i);
         }
     } else if (warp >= 2 && warp < 6) {
         // ================= operand splitters =================
@@ -249,8 +295,8 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
                     const float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        hi[q4 * 4 + e] = rna_tf32(x[e]);
-                        lo[q4 * 4 + e] = rna_tf32(x[e] - hi[q4 * 4 + e]);
+                        hi[q4 * 4 + e] = x[e];
+                        lo[q4 * 4 + e] = tf32_lo(x[e]);
                     }
                 }
                 tmem_st16(trow + kColQHi + (uint32_t)(c16 * 16), hi);
@@ -263,123 +309,166 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
         for (int j = 0; j < n_blocks; ++j) {
             const int s = j % kStages;
             mbar_wait(bar(kKvFull + s), (j / kStages) & 1);
-            float4 *raw = reinterpret_cast<float4 *>(smem + kOffStage + s * kStageBytes);
+            stamp(a.dbg, tr, kEvKvFull, j);
+            const float4 *raw = reinterpret_cast<const float4 *>(smem + kOffStage + s * kStageBytes);
             float4 *twin = reinterpret_cast<float4 *>(smem + kOffStage + s * kStageBytes + kRawBytes);
             constexpr int kIters = kRawBytes / 16 / 128;  // 16 float4 per thread
 #pragma unroll 4
-            for (int it = 0; it < kIters; ++it) {
+            for (int it = (a.skip & 8) ? kIters : 0; it < kIters; ++it) {
                 const int idx = it * 128 + t;
                 const float4 v = raw[idx];
-                float4 h, l;
-                h.x = rna_tf32(v.x), h.y = rna_tf32(v.y), h.z = rna_tf32(v.z), h.w = rna_tf32(v.w);
-                l.x = rna_tf32(v.x - h.x), l.y = rna_tf32(v.y - h.y), l.z = rna_tf32(v.z - h.z), l.w = rna_tf32(v.w - h.w);
-                raw[idx] = h;
-                twin[idx] = l;
+                twin[idx] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));  // hi = the raw tile
             }
             fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
             mbar_arrive(bar(kKvSplit + s));
+            stamp(a.dbg, tr, kEvSplitDone, j);
         }
-    } else if (warp >= 6) {
-        // ================= softmax + epilogue: thread <-> query row =================
+    } else if (warp >= 6 && warp < 10) {
+        // ================= softmax: thread <-> query row =================
         const int row = (warp & 3) * 32 + lane;
         const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const float c = a.scale_log2;
+        float *factor = reinterpret_cast<float *>(smem + kOffFactor);  // [4][128] rescale factors, ring over blocks
         float m_ref = 0.f, l_sum = 0.f;
-        float acc[4][16];  // this row of O, summed over key blocks in fp32 (round-to-nearest)
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-            for (int e = 0; e < 16; ++e) acc[q][e] = 0.f;
-        int folded = 0;  // key blocks whose P V partial has been added into acc
-        // acc += T[i & 1] once P_i V_i has landed
-        auto fold = [&](int i) {
-            mbar_wait(bar(kPvDone + (i & 1)), (i >> 1) & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float t[16];
-                tmem_ld16_issue(trow + kColT + (uint32_t)((i & 1) * kHeadDim + q * 16), t);
-                tmem_ld_wait(t);
-#pragma unroll
-                for (int e = 0; e < 16; ++e) acc[q][e] += t[e];
-            }
-        };
         for (int j = 0; j < n_blocks; ++j) {
             const int b = j & 1;
+            const int n_valid = min(kKeys, a.n_ctx - j * kKeys);  // < 64 only for the last block
             mbar_wait(bar(kSFull + b), (j >> 1) & 1);
             tc_fence_after();
+            stamp(a.dbg, tr, kEvSFull, j);
             const uint32_t s_col = trow + kColS + (uint32_t)b * kKeys;
             float sv[4][16];
 #pragma unroll
             for (int q = 0; q < 4; ++q) tmem_ld16_issue(s_col + (uint32_t)(q * 16), sv[q]);
+            if (a.dbg && j == 0 && blockIdx.x + blockIdx.y + blockIdx.z == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) tmem_ld_wait(sv[q]);
-            if (a.dbg && j == 0 && blockIdx.x + blockIdx.y + blockIdx.z == 0)
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
+                for (int q = 0; q < 4; ++q) {
+                    tmem_ld_wait(sv[q]);
 #pragma unroll
                     for (int e = 0; e < 16; ++e) a.dbg[row * 64 + q * 16 + e] = sv[q][e];
-            const int n_valid = min(kKeys, a.n_ctx - j * kKeys);  // < 64 only for the last block
-            float bm = -INFINITY;
+                }
+            }
+            // Streaming pass against the CURRENT reference: p = 2^(s c - m_ref) and the block maximum are
+            // computed together, chunk by chunk as the tensor-memory loads land (four independent chains).
+            float bmax[4], lpart[4];
+            const float neg_m = -m_ref;
             if (n_valid == kKeys) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
+                for (int q = 0; q < 4; ++q) {
+                    tmem_ld_wait(sv[q]);
+                    float mx = sv[q][0], ls = 0.f;
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) bm = fmaxf(bm, sv[q][e]);
-            } else {
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-#pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        if (q * 16 + e < n_valid) bm = fmaxf(bm, sv[q][e]);
-            }
-            bm *= c;
-            if (j == 0) {
-                m_ref = bm;
-            } else {
-                const bool need = bm > m_ref + kRescaleGap;
-                if (__any_sync(0xffffffffu, need)) {
-                    // rare: move the reference.  Everything accumulated so far (including the partial of
-                    // block j-1, which was computed against the old reference) is rescaled in registers.
-                    if (folded < j) {
-                        fold(j - 1);
-                        folded = j;
+                    for (int e = 0; e < 16; ++e) {
+                        mx = fmaxf(mx, sv[q][e]);
+                        sv[q][e] = ex2_approx(fmaf(sv[q][e], c, neg_m));
+                        ls += sv[q][e];
                     }
-                    const float nm = need ? bm : m_ref;
-                    const float f = ex2_approx(m_ref - nm);
+                    bmax[q] = mx;
+                    lpart[q] = ls;
+                }
+            } else {  // last block of a context that is not a multiple of 64: keys >= n_valid do not exist
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
+                for (int q = 0; q < 4; ++q) {
+                    tmem_ld_wait(sv[q]);
+                    float mx = -INFINITY, ls = 0.f;
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) acc[q][e] *= f;
-                    l_sum *= f;
-                    m_ref = nm;
+                    for (int e = 0; e < 16; ++e) {
+                        const bool ok = q * 16 + e < n_valid;
+                        mx = ok ? fmaxf(mx, sv[q][e]) : mx;
+                        sv[q][e] = ok ? ex2_approx(fmaf(sv[q][e], c, neg_m)) : 0.f;
+                        ls += sv[q][e];
+                    }
+                    bmax[q] = mx;
+                    lpart[q] = ls;
                 }
             }
-            // P_lo[b] and T[b] are free: P V of block j-2 completed before it was folded (iteration j-1)
+            const float bm = fmaxf(fmaxf(bmax[0], bmax[1]), fmaxf(bmax[2], bmax[3])) * c;
+            float f = 1.f;
+            // Block 0 has no reference yet; later blocks move it only when they exceed it by 2^32 (rare).
+            const bool need = j == 0 || bm > m_ref + kRescaleGap;
+            if (__any_sync(0xffffffffu, need)) {
+                if (need) {
+                    f = j == 0 ? 1.f : ex2_approx(m_ref - bm);
+                    m_ref = bm;
+                    l_sum *= f;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tmem_ld16_issue(s_col + (uint32_t)(q * 16), sv[q]);  // S is still intact
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    tmem_ld_wait(sv[q]);
+                    float ls = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const bool ok = q * 16 + e < n_valid;
+                        sv[q][e] = ok ? ex2_approx(fmaf(sv[q][e], c, -m_ref)) : 0.f;
+                        ls += sv[q][e];
+                    }
+                    lpart[q] = ls;
+                }
+            }
+            l_sum += (lpart[0] + lpart[1]) + (lpart[2] + lpart[3]);
+            stamp(a.dbg, tr, kEvExpDone, j);
+            factor[(j & 3) * kQRows + row] = f;  // read by the accumulate thread of this row after P V of block j
+            if (j >= 2) {  // P V of block j-2 has finished reading P_hi (= S[b]) and P_lo[b]
+                mbar_wait(bar(kPvDone + b), ((j - 2) >> 1) & 1);
+                tc_fence_after();
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                float hi[16], lo[16];
+                float lo[16];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    float p = ex2_approx(fmaf(sv[q][e], c, -m_ref));
-                    if (q * 16 + e >= n_valid) p = 0.f;
-                    l_sum += p;
-                    hi[e] = rna_tf32(p);
-                    lo[e] = rna_tf32(p - hi[e]);
-                }
-                tmem_st16(s_col + (uint32_t)(q * 16), hi);
+                for (int e = 0; e < 16; ++e) lo[e] = tf32_lo(sv[q][e]);
+                tmem_st16(s_col + (uint32_t)(q * 16), sv[q]);  // P_hi = p as is (the tensor core chops it)
                 tmem_st16(trow + kColPLo + (uint32_t)(b * kKeys + q * 16), lo);
             }
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(bar(kPReady + b));
-            if (j >= 1 && folded < j) {  // off the critical path: the tensor pipe is busy with Q K_{j+1}^T
-                fold(j - 1);
-                folded = j;
-            }
+            stamp(a.dbg, tr, kEvPArrive, j);
         }
-        fold(n_blocks - 1);
+        factor[4 * kQRows + row] = l_sum;
+        mbar_arrive(bar(kLReady));
+    } else if (warp >= 10) {
+        // ================= accumulate + epilogue: thread <-> query row =================
+        // acc = this row of O, summed over key blocks in fp32 registers with round-to-nearest.
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const float *factor = reinterpret_cast<const float *>(smem + kOffFactor);
+        float acc[4][16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[q][e] = 0.f;
+        for (int j = 0; j < n_blocks; ++j) {
+            const int b = j & 1;
+            mbar_wait(bar(kPvDone + b), (j >> 1) & 1);
+            tc_fence_after();
+            stamp(a.dbg, tr, kEvPvDone, j);
+            float t[2][16];  // two chunks in flight
+            const uint32_t t_col = trow + kColT + (uint32_t)(b * kHeadDim);
+            tmem_ld16_issue(t_col, t[0]);
+            const float f = *reinterpret_cast<const volatile float *>(&factor[(j & 3) * kQRows + row]);
+            if (f != 1.f) {  // the reference moved at block j: everything before it is rescaled
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) acc[q][e] *= f;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q + 1 < 4) tmem_ld16_issue(t_col + (uint32_t)((q + 1) * 16), t[(q + 1) & 1]);
+                tmem_ld_wait(t[q & 1]);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acc[q][e] += t[q & 1][e];
+            }
+            tc_fence_before();
+            mbar_arrive(bar(kTFree + b));
+            stamp(a.dbg, tr, kEvFoldDone, j);
+        }
         // ---- epilogue: O / l -> global
+        mbar_wait(bar(kLReady), 0);
+        const float l_sum = *reinterpret_cast<const volatile float *>(&factor[4 * kQRows + row]);
         const float inv = 1.f / l_sum;
         const bool row_ok = q0 + row < a.n_ctx;
         float *dst = a.out + ((int64_t)batch * a.n_ctx + q0 + row) * a.ld_out + col0;
@@ -389,7 +478,6 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
 #pragma unroll
                 for (int e = 0; e < 16; ++e) a.dbg[8192 + row * 64 + q * 16 + e] = acc[q][e];
                 a.dbg[16384 + row] = l_sum;
-                a.dbg[16512 + row] = m_ref;
             }
             if (row_ok) {
 #pragma unroll
@@ -461,6 +549,14 @@ int launch_encoder_attention(const float *d_q, const float *d_k, const float *d_
     a.ld_out = ld_out;
     a.n_ctx = n_ctx;
     a.dbg = g_enc_attn_dbg;
+    {
+        static int skip = -1;
+        if (skip < 0) {
+            const char *e = getenv("WCA_EA_SKIP");
+            skip = e ? atoi(e) : 0;
+        }
+        a.skip = (unsigned)skip;
+    }
     a.scale_log2 = (float)(0.125 * 1.4426950408889634);  // Dh^-1/2 (= (Dh^-1/4)^2 of upstream) * log2(e)
     WCA_CUDA(cudaFuncSetAttribute(ea::enc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ea::kSmemBytes));
     const dim3 grid((unsigned)((n_ctx + ea::kQRows - 1) / ea::kQRows), (unsigned)n_heads, (unsigned)n_batch);
