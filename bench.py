@@ -92,6 +92,8 @@ def parse():
     ap.add_argument("--medfilt_width", type=int, default=3)
     ap.add_argument("--fp32-gemm", default="bf16x9", choices=["bf16x9", "native"],
                     help="cuBLAS fp32 GEMMs of the upstream linears: BF16x9-emulated fp32 (cuBLAS 12.9) or SIMT SGEMM")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed `value` region (for `ncu --profile-from-start off`)")
     ap.add_argument("--cpu-sample", type=int, default=2, help="utterances timed for cpu_baseline (0 = skip)")
     return ap.parse_args()
 
@@ -324,8 +326,12 @@ def main():
                 local_alignments[(i * args.batch + j) * world + rank] = (r[1], r[2])
 
     launches0 = _cabi.launch_count()
+    if args.profile_range:
+        torch.cuda.profiler.start()
     with ClockSampler(local_rank) as clocks, _cabi.KernelTimer() as kt:
         ms_value, last = timed(step_resident, args.steps, collect)
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     launches = _cabi.launch_count() - launches0
     kernel_ms = kt.summary()
     with ClockSampler(local_rank) as clocks_e2e:
