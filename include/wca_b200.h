@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define WCA_ABI_VERSION 3
-#define WCA_MAX_LAYERS 64      /* large-v3 has 32 */
+#define WCA_MAX_LAYERS 32      /* decoder layers of the largest published Whisper (large-v3) */
 #define WCA_MAX_MEDFILT 31     /* odd widths 1..31 */
 #define WCA_TOKENS_PER_SECOND 50.0 /* whisper.audio.TOKENS_PER_SECOND, timing.py:10,111 */
 

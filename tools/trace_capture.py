@@ -42,12 +42,12 @@ for i in range(4, 16):
 d = lambda a, b: np.nanmean((tr[6:36, EV.index(b)] - tr[6:36, EV.index(a)]))
 print("\nmean cycles over tiles 6..35 (T=%d..%d, F=%d..%d):" % (Ts.min(), Ts.max(), Fs.min(), Fs.max()))
 print(" tile period (MmaIssued[i+1]-MmaIssued[i])  :", np.nanmean(np.diff(tr[6:36, EV.index('MmaIssued')])))
-print(" splitter: AFree->QDone                     :", d("SplAFree", "SplQDone"))
-print(" splitter: QDone->K0Done                    :", d("SplQDone", "SplK0Done"))
-print(" splitter: K0Done->KLast                    :", d("SplK0Done", "SplKLast"))
-print(" mma     : AccEmpty->AReady (wait Q split)  :", d("MmaAccEmpty", "MmaAReady"))
-print(" mma     : AReady->B0 (wait K0 split)       :", d("MmaAReady", "MmaB0"))
-print(" mma     : B0->Issued                       :", d("MmaB0", "MmaIssued"))
+print(" producer: issue(i) - MmaIssued(i-1)        :", np.nanmean(tr[7:36, EV.index('ProdQ')] - tr[6:35, EV.index('MmaIssued')]))
+print(" TMA     : issue -> landed (SplFull)        :", d("ProdQ", "SplFull"))
+print(" splitter: landed -> K slab lo              :", d("SplFull", "SplK0Done"))
+print(" splitter: K slab lo -> Q lo + arrive       :", d("SplK0Done", "SplQDone"))
+print(" mma     : AccEmpty seen -> operands ready  :", d("MmaAccEmpty", "MmaAReady"))
+print(" mma     : operands ready -> 24 MMAs issued :", d("MmaAReady", "MmaIssued"))
 print(" mma->epi: Issued->AccFull seen             :", d("MmaIssued", "EpiAccFull"))
 print(" epilogue: sweep A                          :", d("EpiAccFull", "EpiA"))
 print(" epilogue: xmax exchange                    :", d("EpiA", "EpiXMax"))
@@ -55,5 +55,4 @@ print(" epilogue: sweep B                          :", d("EpiXMax", "EpiB"))
 print(" epilogue: xsum exchange                    :", d("EpiB", "EpiXSum"))
 print(" epilogue: sweep C                          :", d("EpiXSum", "EpiC"))
 print(" epilogue: total AccFull->C                 :", d("EpiAccFull", "EpiC"))
-print(" producer: Q issue -> KLast issue           :", d("ProdQ", "ProdKLast"))
-print(" Q split : AFree->Full | Full->Loaded | Loaded->Stored | Stored->Fenced | Fenced->QDone:", d("SplAFree","SplFull"), d("SplFull","SplLoaded"), d("SplLoaded","SplStored"), d("SplStored","SplFenced"), d("SplFenced","SplQDone"))
+print(" epilogue: C(i) -> AccFull(i+2) (same WG)   :", np.nanmean(tr[8:36, EV.index('EpiAccFull')] - tr[6:34, EV.index('EpiC')]))

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libwca_b200.so")
 WCA_CAPTURE_RAW_LOGITS = 1
 WCA_CAPTURE_FORCE_SIMT = 2
 WCA_CAPTURE_TRACE = 4
-WCA_MAX_LAYERS = 64
+WCA_MAX_LAYERS = 32
 ABI_VERSION = 3
 
 EXPORTS = (

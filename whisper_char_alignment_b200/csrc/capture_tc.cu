@@ -17,15 +17,13 @@
 //               epilogue warpgroup drains the other;
 //   F > 224 : thread-block cluster of 2/4/8 CTAs along frames; per-row max and sum travel
 //               through distributed shared memory, signalled with remote mbarrier arrives;
-//   fp32 in, fp32-grade out on the tensor pipe: operands are split v = hi + lo (hi, lo
-//               rounded to tf32) and lo*hi + hi*lo + hi*hi is accumulated: 3 x 8
-//               tcgen05.mma kind::tf32 per 64-frame chunk, error ~1e-6 relative;
+//   fp32 in, fp32-grade out on the tensor pipe: operands are split v = hi + lo (hi = v as the
+//               tensor core chops it to tf32, lo = v - hi exact) and lo*hi + hi*lo + hi*hi is
+//               accumulated: 3 x 8 tcgen05.mma kind::tf32 of N = all frames of the CTA per head,
+//               error ~1e-6 relative;
 //   TMA     : Q / K tiles arrive as 2-D tensor-map boxes (cp.async.bulk.tensor.2d, 64 rows x
-//               32 floats, 128-byte swizzle, two boxes per 64-row stage) on mbarriers into a
-//               4-stage staging ring; splitter warps rewrite them into the no-swizzle K-major
-//               UMMA layout [k-chunk][8-row group][8 rows][16 B].  (Row-granular
-//               cp.async.bulk copies measured ~75 cycles each in the TMA unit and starved the
-//               pipeline: profiles/r01_capture_tc_v2_*.)
+//               32 floats, 128-byte swizzle) on one mbarrier per tile, directly where the MMA
+//               reads them: the swizzled boxes ARE the UMMA K-major SWIZZLE_128B layout.
 //
 // Roles of the 16 warps of a CTA (one persistent CTA per SM, static tile schedule):
 //   warp 0      TMA producer            warp 1      MMA issuer (one thread)
@@ -49,37 +47,36 @@ constexpr int kOwnCol0 = 16;         // accumulator column of a CTA's first own 
 constexpr int kAccCols = 256;        // columns per accumulator
 constexpr int kMaxOwn = kAccCols - 2 * kHalo;   // 224 own frames per CTA and tile
 constexpr int kTmemCols = 512;
-constexpr int kRowBytes = kHeadDim * 4;          // 256
-constexpr int kStageRows = 64;
+constexpr int kStageRows = 64;                     // rows per TMA box
 constexpr int kBoxCols = 32;                       // floats per TMA box row: 128 B, the swizzle span
-constexpr int kBoxBytes = kStageRows * kBoxCols * 4;     // 8192
-constexpr int kStageBytes = 2 * kBoxBytes;               // 16384: [column half][64 rows][128 B swizzled]
-constexpr int kStages = 4;
-constexpr int kQSplitBytes = kRows * kRowBytes;         // 32768 per hi / lo
-constexpr int kKSplitBytes = kChunk * kRowBytes;        // 16384 per hi / lo per buffer
-constexpr uint32_t kLboQ = kRows * 16;   // bytes between consecutive 16-byte k-chunks (A operand)
-constexpr uint32_t kLboK = kChunk * 16;  // same for the B operand
-constexpr uint32_t kSbo = 128;           // bytes between consecutive 8-row groups
+constexpr int kBoxBytes = kStageRows * kBoxCols * 4;     // 8192: one 64-row x 128-byte box
+constexpr int kQHalfBytes = 2 * kBoxBytes;               // Q tile, one column half: 128 rows x 128 B
+constexpr int kQBytes = 2 * kQHalfBytes;                 // 32768
+constexpr int kMaxChunks = kAccCols / kChunk;            // 4 boxes of 64 frames cover an accumulator
+constexpr int kKHalfBytes = kMaxChunks * kBoxBytes;      // K slab, one column half: 256 frames x 128 B
+constexpr int kKBytes = 2 * kKHalfBytes;                 // 65536
 constexpr int kTilePitch = 17;           // transpose tile pitch (odd: conflict-free column writes)
 constexpr int kSplitThreads = 128;
 constexpr int kEpiThreads = 128;
 
-constexpr int kOffStage = 0;
-constexpr int kOffQHi = kOffStage + kStages * kStageBytes;
-constexpr int kOffQLo = kOffQHi + kQSplitBytes;
-constexpr int kOffKHi = kOffQLo + kQSplitBytes;
-constexpr int kOffKLo = kOffKHi + 2 * kKSplitBytes;
-constexpr int kOffTile = kOffKLo + 2 * kKSplitBytes;            // 8 epilogue warps x 32 x 17 floats
+// Operands live in shared memory exactly as TMA lands them (128-byte swizzle = the UMMA canonical
+// K-major SWIZZLE_128B layout); the `hi` part of the 3 x tf32 split is the tile itself (the tensor
+// core ignores the 13 low mantissa bits), the `lo` part is a twin tile the splitter warps write.
+// One tile = the Q tile (128 token rows) + the whole K slab of the CTA (up to 256 frames), so that a
+// head is 24 MMAs of N = up to 256 instead of 72 of N = 64: with both operands in shared memory an
+// MMA re-reads its 4 KB of A every time, and at N = 64 that made the tensor pipe wait on shared memory.
+constexpr int kOffQHi = 0;
+constexpr int kOffQLo = kOffQHi + kQBytes;
+constexpr int kOffKHi = kOffQLo + kQBytes;
+constexpr int kOffKLo = kOffKHi + kKBytes;
+constexpr int kOffTile = kOffKLo + kKBytes;                     // 8 epilogue warps x 32 x 17 floats
 constexpr int kOffStat = kOffTile + 8 * 32 * kTilePitch * 4;    // smax[2][128], ssum[2][128]
 constexpr int kOffBar = kOffStat + 4 * kRows * 4;
 enum Bar {
-    kStageFull = 0,
-    kStageEmpty = kStageFull + kStages,
-    kAReady = kStageEmpty + kStages,
-    kAFree = kAReady + 1,
-    kBReady = kAFree + 1,
-    kBFree = kBReady + 2,
-    kAccFull = kBFree + 2,
+    kOpFull = 0,                 // TMA -> splitters (transaction bytes): Q tile + K slab landed
+    kOpReady = kOpFull + 1,      // splitters -> MMA issuer: lo twins written
+    kOpFree = kOpReady + 1,      // MMA (tcgen05.commit) -> TMA producer: operands no longer read
+    kAccFull = kOpFree + 1,
     kAccEmpty = kAccFull + 2,
     kXMax = kAccEmpty + 2,
     kXSum = kXMax + 2,
@@ -102,9 +99,12 @@ __device__ __forceinline__ void stamp(bool on, uint32_t tile_seq, int ev) {
 }
 
 // ------------------------------------------------------------------ tile geometry
+// (rows, H*64) fp32 matrices, boxes of 32 floats (128 B, the swizzle span) x 64 / 128 / 192 / 256 rows:
+// one TMA instruction costs ~150 cycles of the producer lane whatever it moves, so a tile is fetched
+// with the tallest box that fits (K slab: one box per column half).
 struct TensorMaps {
-    CUtensorMap q[WCA_MAX_LAYERS];  // (rows, H*64) fp32 matrices, box 64 rows x 32 floats, 128B swizzle
-    CUtensorMap k[WCA_MAX_LAYERS];
+    CUtensorMap q[2][WCA_MAX_LAYERS];  // [box rows / 64 - 1]
+    CUtensorMap k[4][WCA_MAX_LAYERS];
 };
 
 struct KernelArgs {
@@ -161,72 +161,18 @@ __device__ __forceinline__ Geo decode_tile(const KernelArgs &a, int tile, uint32
     return g;
 }
 
-// Staging items of one tile, in ring order: K chunk 0, then the Q halves, then K chunks 1..
-// (K0 first so that it can be split while the previous tile's MMAs still read the Q buffers).
-struct Item {
-    bool is_q;
-    int index;  // Q half (0/1) or K chunk
-};
-__device__ __forceinline__ int tile_items(const Geo &g) { return g.n_chunks + (g.rows_valid > kStageRows ? 2 : 1); }
-__device__ __forceinline__ Item tile_item(const Geo &g, int i) {
-    const int n_q = g.rows_valid > kStageRows ? 2 : 1;
-    Item it;
-    it.is_q = i >= 1 && i <= n_q;
-    it.index = i == 0 ? 0 : (it.is_q ? i - 1 : i - n_q);
-    return it;
-}
-
-// ------------------------------------------------------------------ role bodies
-// One elected lane arms the stage barrier and issues the two column-half boxes of a 64-row tile.
-__device__ __forceinline__ void producer_item(uint32_t stage, uint32_t bar_full, uint32_t bar_empty, uint32_t n_item,
-                                              const CUtensorMap *map, int col0, int row0, int lane) {
-    mbar_wait(bar_empty, ((n_item / kStages) & 1u) ^ 1u);  // first lap passes immediately
-    if (lane == 0) {
-        mbar_expect_tx(bar_full, kStageBytes);  // boxes are always full: rows past the matrix end read as zero
-        tma_load_box(stage, map, col0, row0, bar_full);
-        tma_load_box(stage + kBoxBytes, map, col0 + kBoxCols, row0, bar_full);
-    }
-    __syncwarp();
-}
-
-// 128 splitter threads: staging tile (64 rows) -> scaled hi / lo parts in UMMA no-swizzle layout.
-__device__ __forceinline__ void split_stage(const unsigned char *stage, unsigned char *hi, unsigned char *lo,
-                                            uint32_t lbo, int row_off, float s, int t, bool mirror = false,
-                                            bool tr = false, uint32_t seq = 0) {
-    constexpr int kIters = (kStageRows * 16) / kSplitThreads;  // 8 float4 per thread
-    // e = it * 128 + t  ->  row = t & 63 (fixed per thread), 16-byte chunk ch = 2 * it + (t >> 6)
-    const int row = t & (kStageRows - 1);
-    const int ch0 = t >> 6;
+// 128 splitter threads: lo twin of kBytes of a tile, linear sweep (same swizzled position, conflict-free).
+template <int kBytes>
+__device__ __forceinline__ void split_lo(const unsigned char *hi, unsigned char *lo, int t) {
+    constexpr int kIters = kBytes / 16 / kSplitThreads;
+    const float4 *src = reinterpret_cast<const float4 *>(hi);
+    float4 *dst = reinterpret_cast<float4 *>(lo);
     float4 v[kIters];
 #pragma unroll
-    for (int it = 0; it < kIters; ++it) {  // all loads in flight before any arithmetic
-        const int ch = 2 * it + ch0;
-        // 128-byte swizzle of the TMA box: 16-byte chunk c of row r sits at chunk position c ^ (r & 7)
-        v[it] = *reinterpret_cast<const float4 *>(stage + (ch >> 3) * kBoxBytes + row * 128 + (((ch & 7) ^ (row & 7)) << 4));
-    }
-    if (tr && v[0].x != 1e30f) stamp(tr, seq, kEvSplLoaded);
+    for (int it = 0; it < kIters; ++it) v[it] = src[it * kSplitThreads + t];  // all loads in flight first
 #pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-        const int ch = 2 * it + ch0;
-        const float x[4] = {v[it].x * s, v[it].y * s, v[it].z * s, v[it].w * s};
-        float h[4], l[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            // round-to-nearest onto the 10-bit tf32 mantissa; x - h is exact in fp32 (may be negative)
-            h[c] = __uint_as_float((__float_as_uint(x[c]) + 0x1000u) & 0xFFFFE000u);
-            l[c] = __uint_as_float((__float_as_uint(x[c] - h[c]) + 0x1000u) & 0xFFFFE000u);
-        }
-        const uint32_t off = (uint32_t)ch * lbo + (uint32_t)(row + row_off) * 16u;
-        *reinterpret_cast<float4 *>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<float4 *>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
-        if (mirror) {  // second copy of the token rows in A rows 64..127 (see Geo::dup)
-            *reinterpret_cast<float4 *>(hi + off + kStageRows * 16u) = make_float4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<float4 *>(lo + off + kStageRows * 16u) = make_float4(l[0], l[1], l[2], l[3]);
-        }
-    }
-    stamp(tr, seq, kEvSplStored);
-    fence_proxy_async_smem();  // generic-proxy stores must be visible to the tensor core's async proxy
-    stamp(tr, seq, kEvSplFenced);
+    for (int it = 0; it < kIters; ++it)
+        dst[it * kSplitThreads + t] = make_float4(tf32_lo(v[it].x), tf32_lo(v[it].y), tf32_lo(v[it].z), tf32_lo(v[it].w));
 }
 
 // Sliding median over a 16-column block with its neighbour blocks; every index is a compile
@@ -274,7 +220,7 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
     const uint32_t bar_xmax = smem_u32(smem + kOffBar) + 8u * (kXMax + grp);
     const uint32_t bar_xsum = smem_u32(smem + kOffBar) + 8u * (kXSum + grp);
 
-    float inv_sum = 1.f;
+    float inv_sum = a.s;  // raw-logit mode: only the 2^-3 of the operand scaling is applied
     if (!a.raw_logits) {
         float row_max = -INFINITY;
         if (rows_live && g.half > 0) {
@@ -446,15 +392,10 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
 
     // ---- setup ------------------------------------------------------------------------
     if (tid == 0) {
-        for (int i = 0; i < kStages; ++i) {
-            mbar_init(bar(kStageFull + i), 1);
-            mbar_init(bar(kStageEmpty + i), kSplitThreads);
-        }
-        mbar_init(bar(kAReady), kSplitThreads);
-        mbar_init(bar(kAFree), 1);
+        mbar_init(bar(kOpFull), 1);
+        mbar_init(bar(kOpReady), kSplitThreads);
+        mbar_init(bar(kOpFree), 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(bar(kBReady + i), kSplitThreads);
-            mbar_init(bar(kBFree + i), 1);
             mbar_init(bar(kAccFull + i), 1);
             mbar_init(bar(kAccEmpty + i), kEpiThreads);
             mbar_init(bar(kXMax + i), csize);
@@ -473,118 +414,116 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
     cluster_sync_all();  // peers' barriers are initialised before anyone arrives remotely
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        uint32_t n_item = 0, seq = 0;
+        // ================= TMA producer: boxes land directly in the operand buffers =================
+        uint32_t n_tile = 0;
         const bool tr = a.trace && blockIdx.x == 0 && lane == 0;
-        const uint32_t stage0 = smem_u32(smem + kOffStage);
+        const uint32_t q_hi = smem_u32(smem + kOffQHi), k_hi = smem_u32(smem + kOffKHi);
         for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
             const Geo g = decode_tile<W>(a, tile, crank, csize);
             if (!g.live || g.n_own == 0) continue;
-            const int n_items = tile_items(g);
-            for (int i = 0; i < n_items; ++i) {
-                const Item item = tile_item(g, i);
-                const uint32_t s = n_item % kStages;
-                if (item.is_q)
-                    producer_item(stage0 + s * kStageBytes, bar(kStageFull + s), bar(kStageEmpty + s), n_item,
-                                  &maps.q[g.layer], g.col0, g.qrow0 + item.index * kStageRows, lane);
-                else
-                    producer_item(stage0 + s * kStageBytes, bar(kStageFull + s), bar(kStageEmpty + s), n_item,
-                                  &maps.k[g.layer], g.col0, g.krow0 + g.m0 + item.index * kChunk, lane);
-                ++n_item;
-                stamp(tr, seq, item.is_q ? kEvProdQ : (item.index == 0 ? kEvProdK0 : kEvProdKLast));
+            mbar_wait(bar(kOpFree), (n_tile & 1u) ^ 1u);  // MMAs of the previous tile no longer read Q / K (first lap passes)
+            if (lane == 0) {
+                // Q rows 64..127: the next 64 token rows, or (Geo::dup) a second copy of rows 0..63; with <= 64
+                // rows and no mirroring the upper half is left as it is (nobody reads those lanes)
+                const bool upper = g.dup || g.rows_valid > kStageRows;
+                // boxes are always full: rows past the matrix end read as zero
+                mbar_expect_tx(bar(kOpFull), (upper ? kQBytes : kQBytes / 2) + g.n_chunks * 2 * kBoxBytes);
+                const CUtensorMap *kmap = &maps.k[g.n_chunks - 1][g.layer];   // box = n_chunks * 64 frames
+                const CUtensorMap *qmap = &maps.q[(upper && !g.dup) ? 1 : 0][g.layer];
+                for (int half = 0; half < 2; ++half) {
+                    tma_load_box(k_hi + half * kKHalfBytes, kmap, g.col0 + half * kBoxCols, g.krow0 + g.m0, bar(kOpFull));
+                    tma_load_box(q_hi + half * kQHalfBytes, qmap, g.col0 + half * kBoxCols, g.qrow0, bar(kOpFull));
+                    if (g.dup)
+                        tma_load_box(q_hi + half * kQHalfBytes + kBoxBytes, qmap, g.col0 + half * kBoxCols, g.qrow0,
+                                     bar(kOpFull));
+                }
             }
-            ++seq;
+            __syncwarp();
+            stamp(tr, n_tile, kEvProdQ);
+            ++n_tile;
+            // While this tile is split, multiplied and filtered, pull the next tile's boxes into L2: the
+            // operand buffers are single (shared memory is full), so the next load can only be issued once
+            // this tile's MMAs are done, and its latency is then an L2 hit instead of an HBM round trip.
+            for (int nt = tile + n_clusters; nt < a.n_tiles; nt += n_clusters) {
+                const Geo h = decode_tile<W>(a, nt, crank, csize);
+                if (!h.live || h.n_own == 0) continue;
+                if (lane == 0) {
+                    const CUtensorMap *kmap = &maps.k[h.n_chunks - 1][h.layer];
+                    const CUtensorMap *qmap = &maps.q[(!h.dup && h.rows_valid > kStageRows) ? 1 : 0][h.layer];
+                    for (int half = 0; half < 2; ++half) {
+                        tma_prefetch_box(kmap, h.col0 + half * kBoxCols, h.krow0 + h.m0);
+                        tma_prefetch_box(qmap, h.col0 + half * kBoxCols, h.qrow0);
+                    }
+                }
+                __syncwarp();
+                break;
+            }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer: warp-uniform control flow, one elected lane issues =================
-        uint32_t n_tile = 0, n_chunk = 0, acc_use[2] = {0, 0}, it = 0;
+        // ================= MMA issuer: the whole warp runs the loop, one elected lane issues =================
+        // (only the tcgen05.mma itself is predicated: descriptor arithmetic stays on the uniform datapath)
+        uint32_t n_tile = 0, acc_use0 = 0, acc_use1 = 0, it = 0;
         const bool tr = a.trace && blockIdx.x == 0 && lane == 0;
-        const uint32_t a_hi = smem_u32(smem + kOffQHi), a_lo = smem_u32(smem + kOffQLo);
+        const uint32_t elected = elect_one() ? 1u : 0u;
+        const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+        // K-major, 128-byte swizzle: 8-row groups are 1024 B apart; 8 tf32 = 32 B along the row, the second
+        // column half is the next half-tile (A: +16 KB, B: +32 KB)
+        const uint64_t da_hi = smem_desc_sw128(smem_u32(smem + kOffQHi), 16, 1024);
+        const uint64_t da_lo = smem_desc_sw128(smem_u32(smem + kOffQLo), 16, 1024);
+        const uint64_t db_hi = smem_desc_sw128(smem_u32(smem + kOffKHi), 16, 1024);
+        const uint64_t db_lo = smem_desc_sw128(smem_u32(smem + kOffKLo), 16, 1024);
         for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
             const Geo g = decode_tile<W>(a, tile, crank, csize);
             if (!g.live) continue;
             const uint32_t buf = it & 1u;
             ++it;
             if (g.n_own == 0) continue;
-            mbar_wait(bar(kAccEmpty + buf), (acc_use[buf] & 1u) ^ 1u);  // epilogue drained this accumulator
-            ++acc_use[buf];
+            const uint32_t use = buf ? acc_use1 : acc_use0;
+            mbar_wait(bar(kAccEmpty + buf), (use & 1u) ^ 1u);  // epilogue drained this accumulator
+            if (buf) ++acc_use1; else ++acc_use0;
             stamp(tr, n_tile, kEvMmaAccEmpty);
-            mbar_wait(bar(kAReady), n_tile & 1u);
+            mbar_wait(bar(kOpReady), n_tile & 1u);
             stamp(tr, n_tile, kEvMmaAReady);
-            ++n_tile;
-            for (int j = 0; j < g.n_chunks; ++j) {
-                const uint32_t kb = n_chunk & 1u;
-                mbar_wait(bar(kBReady + kb), (n_chunk >> 1) & 1u);
-                ++n_chunk;
-                if (j == 0) stamp(tr, n_tile - 1, kEvMmaB0);
-                tc_fence_after();
-                const int n_cols = (min(kChunk, g.n_mma - j * kChunk) + 15) & ~15;  // UMMA N: multiple of 16
-                const uint32_t idesc = instr_desc_tf32(kRows, n_cols);
-                const uint32_t d = tmem_base + buf * kAccCols + (uint32_t)(g.mcol0 + j * kChunk);
-                const uint32_t b_hi = smem_u32(smem + kOffKHi) + kb * kKSplitBytes;
-                const uint32_t b_lo = smem_u32(smem + kOffKLo) + kb * kKSplitBytes;
-                if (elect_one()) {
-                    // small terms first: lo*hi, hi*lo, then hi*hi
+            tc_fence_after();
+            const int n_cols = min(kAccCols, (g.n_mma + 15) & ~15);  // UMMA N: multiple of 16
+            const uint32_t idesc = instr_desc_tf32(kRows, n_cols);
+            const uint32_t d = tm + buf * kAccCols + (uint32_t)g.mcol0;
+            // small terms first: lo*hi, hi*lo, then hi*hi
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint64_t da = smem_desc(pass == 0 ? a_lo : a_hi, kLboQ, kSbo);
-                        const uint64_t db = smem_desc(pass == 1 ? b_lo : b_hi, kLboK, kSbo);
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint64_t da = pass == 0 ? da_lo : da_hi;
+                const uint64_t db = pass == 1 ? db_lo : db_hi;
 #pragma unroll
-                        for (int ks = 0; ks < kHeadDim / 8; ++ks)  // K = 8 tf32 = two 16-byte k-chunks per instruction
-                            umma_tf32(d, da + (uint64_t)(ks * ((2 * kLboQ) >> 4)), db + (uint64_t)(ks * ((2 * kLboK) >> 4)),
-                                      idesc, (pass | ks) != 0);
-                    }
-                    umma_commit(bar(kBFree + kb));
-                    if (j == g.n_chunks - 1) {
-                        umma_commit(bar(kAFree));
-                        umma_commit(bar(kAccFull + buf));
-                    }
-                }
-                __syncwarp();
+                for (int ks = 0; ks < kHeadDim / 8; ++ks)
+                    umma_tf32_ss_if(d, da + (uint64_t)(((ks >> 2) * kQHalfBytes + (ks & 3) * 32) >> 4),
+                                    db + (uint64_t)(((ks >> 2) * kKHalfBytes + (ks & 3) * 32) >> 4), idesc, (pass | ks) != 0,
+                                    elected);
             }
-            stamp(tr, n_tile - 1, kEvMmaIssued);
+            umma_commit_if(bar(kOpFree), elected);
+            umma_commit_if(bar(kAccFull + buf), elected);
+            stamp(tr, n_tile, kEvMmaIssued);
+            ++n_tile;
         }
     } else if (warp >= 4 && warp < 8) {
-        // ================= operand splitters =================
+        // ================= operand splitters: write the lo twins =================
         const int t = tid - 4 * 32;
-        uint32_t n_item = 0, n_tile = 0, n_chunk = 0;
+        uint32_t n_tile = 0;
         const bool tr = a.trace && blockIdx.x == 0 && t == 0;
         for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
             const Geo g = decode_tile<W>(a, tile, crank, csize);
             if (!g.live || g.n_own == 0) continue;
-            const int n_items = tile_items(g);
-            const int n_q = g.rows_valid > kStageRows ? 2 : 1;
-            for (int i = 0; i < n_items; ++i) {
-                const Item item = tile_item(g, i);
-                const uint32_t s = n_item % kStages;
-                if (item.is_q) {
-                    if (item.index == 0) {
-                        mbar_wait(bar(kAFree), (n_tile & 1u) ^ 1u);  // MMAs of the previous tile no longer read Q
-                        stamp(tr, n_tile, kEvSplAFree);
-                        ++n_tile;
-                    }
-                    mbar_wait(bar(kStageFull + s), (n_item / kStages) & 1u);
-                    stamp(tr, n_tile - 1, kEvSplFull);
-                    split_stage(smem + kOffStage + s * kStageBytes, smem + kOffQHi, smem + kOffQLo, kLboQ,
-                                item.index * kStageRows, a.s, t, g.dup, tr, n_tile - 1);
-                    mbar_arrive(bar(kStageEmpty + s));
-                    if (item.index == n_q - 1) {
-                        mbar_arrive(bar(kAReady));
-                        stamp(tr, n_tile - 1, kEvSplQDone);
-                    }
-                } else {
-                    const uint32_t kb = n_chunk & 1u;
-                    mbar_wait(bar(kBFree + kb), ((n_chunk >> 1) & 1u) ^ 1u);  // MMA released this K buffer
-                    mbar_wait(bar(kStageFull + s), (n_item / kStages) & 1u);
-                    split_stage(smem + kOffStage + s * kStageBytes, smem + kOffKHi + kb * kKSplitBytes,
-                                smem + kOffKLo + kb * kKSplitBytes, kLboK, 0, a.s, t);
-                    mbar_arrive(bar(kStageEmpty + s));
-                    mbar_arrive(bar(kBReady + kb));
-                    stamp(tr, n_tile - (item.index == 0 ? 0 : 1), item.index == 0 ? kEvSplK0Done : kEvSplKLast);
-                    ++n_chunk;
-                }
-                ++n_item;
-            }
+            mbar_wait(bar(kOpFull), n_tile & 1u);
+            stamp(tr, n_tile, kEvSplFull);
+            for (int half = 0; half < 2; ++half)
+                for (int c = 0; c < g.n_chunks; ++c)
+                    split_lo<kBoxBytes>(smem + kOffKHi + half * kKHalfBytes + c * kBoxBytes,
+                                        smem + kOffKLo + half * kKHalfBytes + c * kBoxBytes, t);
+            stamp(tr, n_tile, kEvSplK0Done);
+            split_lo<kQBytes>(smem + kOffQHi, smem + kOffQLo, t);
+            fence_proxy_async_smem();  // generic-proxy stores must be visible to the tensor core's async proxy
+            mbar_arrive(bar(kOpReady));
+            stamp(tr, n_tile, kEvSplQDone);
+            ++n_tile;
         }
     } else if (warp >= 8) {
         // ================= epilogue warpgroups (A: even tiles, B: odd tiles) =================
@@ -645,10 +584,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int encode_map(EncodeTiledFn encode, CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int64_t ld) {
+static int encode_map(EncodeTiledFn encode, CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int64_t ld,
+                      int box_rows) {
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)tc::kBoxCols, (cuuint32_t)tc::kStageRows};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::kBoxCols, (cuuint32_t)box_rows};
     const cuuint32_t elem[2] = {1, 1};
     const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, elem,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -679,10 +619,16 @@ int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_la
     tc::TensorMaps maps;
     memset(&maps, 0, sizeof(maps));
     for (int l = 0; l < n_layers; ++l) {
-        int rc = encode_map(encode, &maps.q[l], h_q_layers[l], q_rows, (int64_t)n_heads * kHeadDim, ld_q);
-        if (rc) return rc;
-        rc = encode_map(encode, &maps.k[l], h_k_layers[l], k_rows, (int64_t)n_heads * kHeadDim, ld_k);
-        if (rc) return rc;
+        for (int v = 0; v < 2; ++v) {
+            const int rc = encode_map(encode, &maps.q[v][l], h_q_layers[l], q_rows, (int64_t)n_heads * kHeadDim, ld_q,
+                                      (v + 1) * tc::kStageRows);
+            if (rc) return rc;
+        }
+        for (int v = 0; v < 4; ++v) {
+            const int rc = encode_map(encode, &maps.k[v][l], h_k_layers[l], k_rows, (int64_t)n_heads * kHeadDim, ld_k,
+                                      (v + 1) * tc::kStageRows);
+            if (rc) return rc;
+        }
     }
     int csize = 1;
     while (csize < 8 && ((((max_frames + csize - 1) / csize) + 15) & ~15) > tc::kMaxOwn) csize *= 2;
@@ -700,8 +646,10 @@ int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_la
     a.lh_count = lh_count;
     a.tok_blocks = tok_blocks;
     a.n_tiles = (int)tiles;
-    a.s = (float)0.35355339059327373;  // 64 ** -0.25 as the reference's fp32 scalar
-    a.qk_scale = qk_scale;
+    // (q s).(k s) with s = 64^-1/4 is q.k / 8: the operands go to the tensor core unscaled and the exact
+    // power of two is applied after the median filter (scaling by 2^-3 commutes with it bit for bit)
+    a.s = 0.125f;
+    a.qk_scale = qk_scale * 0.125f;
     a.raw_logits = (flags & WCA_CAPTURE_RAW_LOGITS) ? 1 : 0;
     a.trace = (flags & WCA_CAPTURE_TRACE) ? 1 : 0;
     a.dbg = flags & 0xff00u;

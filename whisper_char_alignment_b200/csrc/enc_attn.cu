@@ -84,48 +84,6 @@ __device__ __forceinline__ void tma_load_box3(uint32_t dst, const CUtensorMap *m
         "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
 }
-// 128-byte-swizzled operand descriptor, sm_100 version bit 46.  Layout type (bits 61-63):
-// 2 = SWIZZLE_128B (16-byte chunks XOR row & 7; what K-major tf32 operands use),
-// 1 = SWIZZLE_128B_BASE32B (32-byte chunks XOR row & 3; the ONLY swizzle MN-major tf32 operands
-//     accept -- TMA produces it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
-constexpr uint64_t kSw128 = 2, kSw128Base32 = 1;
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr, uint32_t lbo, uint32_t sbo, uint64_t layout = kSw128) {
-    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (layout << 61);
-}
-// D[tmem] (+)= A[tmem] * B[smem]: A is read from tensor memory (lane = row, one tf32 per column).
-// Executed by the WHOLE warp with `elected` true in one lane: only the instruction is predicated, so
-// the descriptor arithmetic around it stays in convergent code and on the uniform datapath (with the
-// loop inside a divergent `if (elected)` every operand went through R2UR: ~45 cycles per MMA issued,
-// more than the 32 cycles a 128x64x8 tf32 MMA occupies the tensor pipe).
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                             uint32_t accumulate, uint32_t elected) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p, e;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "setp.ne.b32 e, %5, 0;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(elected)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_if(uint32_t bar, uint32_t elected) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred e;\n\t"
-        "setp.ne.b32 e, %1, 0;\n\t"
-        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
-        "}" ::"r"(bar),
-        "r"(elected)
-        : "memory");
-}
-// x = hi + lo for the 3 x tf32 product.  tcgen05.mma.kind::tf32 ignores the 13 low mantissa bits of
-// its operands (measured: with hi = x left as is and lo = x - chop(x) the results are fp32-grade; a
-// rounding tensor core would be off by a tf32 ulp), so hi needs no instruction and no store at all;
-// lo is exact in fp32 and is chopped to its 11 leading bits by the tensor core: |error| <= 2^-21 |x|.
-__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-
 // debug timeline: CTA (0,0,0) stores the low 32 bits of clock64() per (event, key block) behind the dump area
 enum Ev { kEvTmaIssue = 0, kEvKvFull, kEvSplitDone, kEvQkIssue, kEvQkIssued, kEvSFull, kEvExpDone, kEvPArrive, kEvPReady,
           kEvPvIssued, kEvPvDone, kEvFoldDone, kNumEv };
