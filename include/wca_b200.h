@@ -99,21 +99,21 @@ WCA_API int wca_capture_attention(const float *const *h_q_layers, const float *c
  * the device).  Returns the number of int64 entries written (tiles x events) or a status < 0. */
 WCA_API int wca_debug_capture_trace(long long *h_out, int capacity);
 
-/* (1b) Encoder self-attention of the teacher-forced forward (timing.py:57-58 `model(mel, tokens)`;
- * upstream whisper/model.py MultiHeadAttention.qkv_attention as used by AudioEncoder, where
- * n_ctx = 1500): out = softmax(q k^T * Dh^-1/2) v per (batch, head), no mask, fp32 in and out,
- * fp32-grade arithmetic on the tensor cores (3 x tf32 error-compensated products for both
- * contractions).  d_q / d_k / d_v / d_out are row-major matrices of n_batch * n_ctx rows; row
- * (b * n_ctx + t) holds position t of batch item b, columns [h*Dh, (h+1)*Dh) belong to head h;
- * ld_* are the leading dimensions in floats (multiples of 4, pointers 16-byte aligned).
- * The cross-attention maps themselves are NOT produced here (that is wca_capture_attention);
- * this entry point only removes the fp32 CUDA-core attention from the encoder. */
-WCA_API int wca_encoder_attention(const float *d_q, const float *d_k, const float *d_v, float *d_out, int n_batch,
-                          int n_ctx, int n_heads, int head_dim, int64_t ld_q, int64_t ld_k, int64_t ld_v,
-                          int64_t ld_out, wca_stream_t stream);
+/* (1b) Unmasked attention of the teacher-forced forward (timing.py:57-58 `model(mel, tokens)`;
+ * upstream whisper/model.py MultiHeadAttention.qkv_attention): the audio encoder's self-attention
+ * (n_q = n_kv = 1500) and the OUTPUT of the decoder's cross-attention (n_q = tokens, n_kv = 1500):
+ *     out = softmax(q k^T * Dh^-1/2) v   per (batch, head), no mask,
+ * fp32 in and out, fp32-grade arithmetic on the tensor cores (3 x tf32 error-compensated products
+ * for both contractions).  d_q / d_out are row-major matrices of n_batch * n_q rows, d_k / d_v of
+ * n_batch * n_kv rows; row (b * n + t) holds position t of batch item b, columns [h*Dh, (h+1)*Dh)
+ * belong to head h; ld_* are the leading dimensions in floats (multiples of 4, pointers 16-byte
+ * aligned).  The cross-attention MAPS are not produced here (that is wca_capture_attention). */
+WCA_API int wca_full_attention(const float *d_q, const float *d_k, const float *d_v, float *d_out, int n_batch, int n_q,
+                       int n_kv, int n_heads, int head_dim, int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_out,
+                       wca_stream_t stream);
 
 /* Debug only: while a non-null device buffer of >= 20000 floats is registered, CTA (0,0,0) of
- * wca_encoder_attention dumps its first logit block, its un-normalised output rows and the
+ * wca_full_attention dumps its first logit block, its un-normalised output rows and the
  * softmax statistics there (tools/debug_enc_attn.py).  Pass NULL to stop. */
 WCA_API void wca_debug_enc_attn_buffer(float *d_buf);
 

@@ -337,7 +337,7 @@ def _attention_fp64(q, k, v, heads):
 @pytest.mark.parametrize("shape", [(1, 1, 1), (1, 63, 1), (1, 64, 2), (2, 129, 3), (2, 256, 2), (1, 512, 4),
                                    (2, 1500, 2), (1, 1500, 16)], ids=str)
 def test_encoder_attention_matches_fp64_reference(shape, dev):
-    """wca_encoder_attention (tcgen05, 3 x tf32) against torch fp64 on the same inputs: fp32-grade,
+    """wca_full_attention (tcgen05, 3 x tf32) against torch fp64 on the same inputs: fp32-grade,
     i.e. no worse than a few times torch's own fp32 attention.  Covers one-key, ragged last key
     block (63, 129, 1500 = 23*64 + 28), ragged last query block and a strided (fused qkv) input."""
     from whisper_char_alignment_b200 import _cabi
@@ -350,6 +350,23 @@ def test_encoder_attention_matches_fp64_reference(shape, dev):
     ref = _attention_fp64(q, k, v, H)
     err = (out.double() - ref).abs().max().item()
     assert err <= 2e-6 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("shape", [(16, 55, 1500, 16), (3, 1, 1500, 2), (2, 130, 257, 20), (1, 448, 1500, 4)], ids=str)
+def test_cross_attention_output_matches_fp64_reference(shape, dev):
+    """n_q != n_kv: the decoder's cross-attention output (tokens x 1500 frames), medium and large-v3 head counts."""
+    from whisper_char_alignment_b200 import _cabi
+
+    B, Tq, S, H = shape
+    g = torch.Generator(device=dev).manual_seed(Tq * 7 + S)
+    q = torch.randn(B, Tq, H * 64, device=dev, generator=g) * 2
+    k, v = (torch.randn(B, S, H * 64, device=dev, generator=g) for _ in range(2))
+    out = _cabi.full_attention(q, k, v, H)
+    sp = lambda t, n: t.double().view(B, n, H, 64).transpose(1, 2)  # noqa: E731
+    ref = (torch.softmax(sp(q, Tq) @ sp(k, S).transpose(-1, -2) / 8.0, dim=-1) @ sp(v, S)).transpose(1, 2).reshape(B, Tq, H * 64)
+    assert out.shape == ref.shape
+    err = (out.double() - ref).abs().max().item()
+    assert err <= 3e-6 * max(1.0, ref.abs().max().item()), err
 
 
 def test_encoder_attention_large_logits_and_lazy_rescale(dev):
@@ -395,16 +412,20 @@ def test_model_forward_is_the_same_with_either_encoder_attention(oracle_models, 
     model = product_model(oracle_models("mini"), dev)
     g = torch.Generator(device=dev).manual_seed(3)
     mel = torch.randn(2, 80, 2 * model.dims.n_audio_ctx, device=dev, generator=g) * 0.3
+    tokens = torch.randint(0, 50000, (2, 37), device=dev, generator=g)
     keep = whisper_model.ENCODER_ATTENTION
     try:
         with torch.no_grad():
             whisper_model.ENCODER_ATTENTION = "wca"
             xa = model.encoder(mel)
+            la = model.decoder(tokens, xa)
             whisper_model.ENCODER_ATTENTION = "sdpa"
             xb = model.encoder(mel)
+            lb = model.decoder(tokens, xa)
     finally:
         whisper_model.ENCODER_ATTENTION = keep
     torch.testing.assert_close(xa, xb, rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(la, lb, rtol=1e-4, atol=1e-4)
 
 
 # ------------------------------------------------------------------------ BASELINE.json full-size shapes

@@ -23,7 +23,7 @@ WCA_MAX_LAYERS = 32
 ABI_VERSION = 3
 
 EXPORTS = (
-    "wca_abi_version", "wca_last_error", "wca_launch_count", "wca_device_info", "wca_capture_attention", "wca_encoder_attention", "wca_debug_enc_attn_buffer", "wca_debug_capture_trace", "wca_medfilt_softmax",
+    "wca_abi_version", "wca_last_error", "wca_launch_count", "wca_device_info", "wca_capture_attention", "wca_full_attention", "wca_debug_enc_attn_buffer", "wca_debug_capture_trace", "wca_medfilt_softmax",
     "wca_head_scores", "wca_topk_heads", "wca_aggregate_heads", "wca_dtw_workspace_bytes", "wca_dtw_align",
 )
 
@@ -73,7 +73,7 @@ def load() -> ctypes.CDLL:
     lib.wca_device_info.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(i32)]
     lib.wca_capture_attention.argtypes = [vp, vp, i32, i32, i32, i64, i64, i64, i64, vp, i32, i32, i32, i32, f32, vp,
                                           ctypes.c_uint, vp]
-    lib.wca_encoder_attention.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, vp]
+    lib.wca_full_attention.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, vp]
     lib.wca_medfilt_softmax.argtypes = [vp, i64, i64, i32, i32, f32, vp, vp]
     lib.wca_head_scores.argtypes = [vp, vp, i32, i32, i32, i32, f32, f32, f32, vp, vp]
     lib.wca_topk_heads.argtypes = [vp, vp, i32, i32, vp, vp, vp]
@@ -216,25 +216,31 @@ def capture_attention(q_layers: Sequence[torch.Tensor], k_layers: Sequence[torch
         )
 
 
-def encoder_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_heads: int, out: torch.Tensor | None = None):
-    """q, k, v: (batch, n_ctx, n_heads*64) fp32, last dim contiguous, rows evenly strided.
-    Returns softmax(q k^T / 8) v in the same layout (wca_encoder_attention)."""
-    batch, n_ctx, width = q.shape
-    for t, name in ((q, "q"), (k, "k"), (v, "v")):
+def full_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_heads: int, out: torch.Tensor | None = None):
+    """q: (batch, n_q, n_heads*64), k, v: (batch, n_kv, n_heads*64), fp32, last dim contiguous, rows evenly
+    strided.  Returns softmax(q k^T / 8) v as (batch, n_q, n_heads*64) (wca_full_attention)."""
+    batch, n_q, width = q.shape
+    n_kv = k.shape[1]
+    for t, name, rows in ((q, "q", n_q), (k, "k", n_kv), (v, "v", n_kv)):
         if not t.is_cuda or t.dtype != torch.float32:
-            raise WcaError(f"encoder_attention: {name} must be an fp32 CUDA tensor (no CPU fallback exists)")
-        if t.shape != q.shape or t.stride(2) != 1 or t.stride(0) != n_ctx * t.stride(1):
-            raise WcaError(f"encoder_attention: {name} must be (batch, n_ctx, width) with contiguous rows")
+            raise WcaError(f"full_attention: {name} must be an fp32 CUDA tensor (no CPU fallback exists)")
+        if tuple(t.shape) != (batch, rows, width) or t.stride(2) != 1 or t.stride(0) != rows * t.stride(1):
+            raise WcaError(f"full_attention: {name} must be (batch, rows, width) with contiguous rows")
     if out is None:
-        out = torch.empty(batch, n_ctx, width, dtype=torch.float32, device=q.device)
-    with _timed("wca_encoder_attention"):
+        out = torch.empty(batch, n_q, width, dtype=torch.float32, device=q.device)
+    with _timed("wca_full_attention"):
         _check(
-            load().wca_encoder_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), _dev_ptr(out, torch.float32, "out"),
-                                         batch, n_ctx, n_heads, width // n_heads, q.stride(1), k.stride(1), v.stride(1),
-                                         out.stride(1), _stream()),
-            "wca_encoder_attention",
+            load().wca_full_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), _dev_ptr(out, torch.float32, "out"),
+                                      batch, n_q, n_kv, n_heads, width // n_heads, q.stride(1), k.stride(1), v.stride(1),
+                                      out.stride(1), _stream()),
+            "wca_full_attention",
         )
     return out
+
+
+def encoder_attention(q, k, v, n_heads, out=None):
+    """Self-attention special case (n_q == n_kv) of full_attention."""
+    return full_attention(q, k, v, n_heads, out)
 
 
 def medfilt_softmax(x: torch.Tensor, n_rows: int, ld_in: int, n_frames: int, medfilt_width: int, qk_scale: float,

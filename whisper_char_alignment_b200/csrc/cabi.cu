@@ -53,8 +53,8 @@ int64_t dtw_workspace_bytes(int, int, int);
 int launch_dtw_align(const float *, const wca_utt_t *, int, int, int, int, int32_t *, int32_t *, int32_t *, int32_t *,
                      const int32_t *, double *, double *, void *, int64_t, cudaStream_t);
 
-int launch_encoder_attention(const float *, const float *, const float *, float *, int, int, int, int64_t, int64_t, int64_t,
-                             int64_t, cudaStream_t);
+int launch_full_attention(const float *, const float *, const float *, float *, int, int, int, int, int64_t, int64_t, int64_t,
+                          int64_t, cudaStream_t);
 
 void set_enc_attn_debug_buffer(float *);
 
@@ -125,32 +125,33 @@ int wca_capture_attention(const float *const *h_q_layers, const float *const *h_
                                           medfilt_width, qk_scale, sms, st);
 }
 
-int wca_encoder_attention(const float *d_q, const float *d_k, const float *d_v, float *d_out, int n_batch, int n_ctx,
-                          int n_heads, int head_dim, int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_out,
-                          wca_stream_t stream) {
-    WCA_CHECK_ARG(d_q && d_k && d_v && d_out, "wca_encoder_attention: null pointer");
+int wca_full_attention(const float *d_q, const float *d_k, const float *d_v, float *d_out, int n_batch, int n_q, int n_kv,
+                       int n_heads, int head_dim, int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_out,
+                       wca_stream_t stream) {
+    WCA_CHECK_ARG(d_q && d_k && d_v && d_out, "wca_full_attention: null pointer");
     if (head_dim != kHeadDim) {
-        set_error("wca_encoder_attention: head_dim=%d unsupported (every Whisper size uses 64)", head_dim);
+        set_error("wca_full_attention: head_dim=%d unsupported (every Whisper size uses 64)", head_dim);
         return WCA_ERR_UNSUPPORTED;
     }
-    WCA_CHECK_ARG(n_batch >= 0 && n_batch <= 65535 && n_heads >= 1 && n_heads <= 65535 && n_ctx >= 1 && n_ctx < (1 << 24),
-                  "wca_encoder_attention: bad geometry (batch %d, n_ctx %d, heads %d)", n_batch, n_ctx, n_heads);
+    WCA_CHECK_ARG(n_batch >= 0 && n_batch <= 65535 && n_heads >= 1 && n_heads <= 65535 && n_q >= 1 && n_q < (1 << 24) &&
+                      n_kv >= 1 && n_kv < (1 << 24),
+                  "wca_full_attention: bad geometry (batch %d, n_q %d, n_kv %d, heads %d)", n_batch, n_q, n_kv, n_heads);
     const int64_t width = (int64_t)n_heads * head_dim;
     WCA_CHECK_ARG(ld_q >= width && ld_k >= width && ld_v >= width && ld_out >= width && ld_q % 4 == 0 && ld_k % 4 == 0 &&
                       ld_v % 4 == 0 && ld_out % 4 == 0,
-                  "wca_encoder_attention: leading dimensions must cover H*Dh=%lld and be multiples of 4", (long long)width);
+                  "wca_full_attention: leading dimensions must cover H*Dh=%lld and be multiples of 4", (long long)width);
     WCA_CHECK_ARG(((uintptr_t)d_q | (uintptr_t)d_k | (uintptr_t)d_v | (uintptr_t)d_out) % 16 == 0,
-                  "wca_encoder_attention: pointers must be 16-byte aligned");
+                  "wca_full_attention: pointers must be 16-byte aligned");
     if (n_batch == 0) return WCA_OK;
     int cc = 0;
     int rc = device_sm_count(nullptr, &cc);
     if (rc) return rc;
     if (cc < 100) {
-        set_error("wca_encoder_attention: needs compute capability 10.x (tcgen05), device is %d", cc);
+        set_error("wca_full_attention: needs compute capability 10.x (tcgen05), device is %d", cc);
         return WCA_ERR_NO_DEVICE;
     }
-    return launch_encoder_attention(d_q, d_k, d_v, d_out, n_batch, n_ctx, n_heads, ld_q, ld_k, ld_v, ld_out,
-                                    static_cast<cudaStream_t>(stream));
+    return launch_full_attention(d_q, d_k, d_v, d_out, n_batch, n_q, n_kv, n_heads, ld_q, ld_k, ld_v, ld_out,
+                                 static_cast<cudaStream_t>(stream));
 }
 
 void wca_debug_enc_attn_buffer(float *d_buf) { set_enc_attn_debug_buffer(d_buf); }

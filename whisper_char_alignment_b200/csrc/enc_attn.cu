@@ -1,4 +1,5 @@
-// tcgen05 / TMEM / TMA non-causal attention for the Whisper audio encoder, fp32 in / fp32-grade out.
+// tcgen05 / TMEM / TMA unmasked attention (the Whisper audio encoder's self-attention and the decoder's
+// cross-attention OUTPUT), fp32 in / fp32-grade out.
 //
 // Row a2 of the scope table (the teacher-forced forward, reference timing.py:57-58): the
 // reference runs the encoder's 1500 x 1500 self-attention in fp32 (upstream
@@ -99,7 +100,7 @@ struct Maps {
 struct Args {
     float *out;
     int64_t ld_out;
-    int n_ctx;
+    int n_q, n_ctx;    // query rows and key/value rows per batch item
     float scale_log2;  // Dh^-1/2 * log2(e)
     unsigned skip;     // debug only (env WCA_EA_SKIP): 2 P V MMAs, 4 Q K^T MMAs, 8 operand split
     float *dbg;        // debug only (wca_debug_enc_attn_buffer): CTA (0,0,0) dumps S of block 0, raw O, l, m
@@ -428,8 +429,8 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
         mbar_wait(bar(kLReady), 0);
         const float l_sum = *reinterpret_cast<const volatile float *>(&factor[4 * kQRows + row]);
         const float inv = 1.f / l_sum;
-        const bool row_ok = q0 + row < a.n_ctx;
-        float *dst = a.out + ((int64_t)batch * a.n_ctx + q0 + row) * a.ld_out + col0;
+        const bool row_ok = q0 + row < a.n_q;
+        float *dst = a.out + ((int64_t)batch * a.n_q + q0 + row) * a.ld_out + col0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             if (a.dbg && blockIdx.x + blockIdx.y + blockIdx.z == 0) {
@@ -480,15 +481,15 @@ static int encode_map3(EncodeTiledFn encode, CUtensorMap *map, const float *base
 static float *g_enc_attn_dbg = nullptr;
 void set_enc_attn_debug_buffer(float *d_buf) { g_enc_attn_dbg = d_buf; }
 
-int launch_encoder_attention(const float *d_q, const float *d_k, const float *d_v, float *d_out, int n_batch, int n_ctx,
-                             int n_heads, int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_out, cudaStream_t stream) {
+int launch_full_attention(const float *d_q, const float *d_k, const float *d_v, float *d_out, int n_batch, int n_q, int n_ctx,
+                          int n_heads, int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_out, cudaStream_t stream) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         WCA_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
         if (qres != cudaDriverEntryPointSuccess || !fn) {
-            set_error("encoder_attention: the driver does not export cuTensorMapEncodeTiled");
+            set_error("full_attention: the driver does not export cuTensorMapEncodeTiled");
             return WCA_ERR_CUDA;
         }
         encode = reinterpret_cast<EncodeTiledFn>(fn);
@@ -496,7 +497,7 @@ int launch_encoder_attention(const float *d_q, const float *d_k, const float *d_
     ea::Maps maps;
     memset(&maps, 0, sizeof(maps));
     const int64_t cols = (int64_t)n_heads * kHeadDim;
-    int rc = encode_map3(encode, &maps.q, d_q, cols, n_ctx, n_batch, ld_q, ea::kQRows, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = encode_map3(encode, &maps.q, d_q, cols, n_q, n_batch, ld_q, ea::kQRows, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     rc = encode_map3(encode, &maps.k, d_k, cols, n_ctx, n_batch, ld_k, ea::kKeys, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -505,6 +506,7 @@ int launch_encoder_attention(const float *d_q, const float *d_k, const float *d_
     ea::Args a;
     a.out = d_out;
     a.ld_out = ld_out;
+    a.n_q = n_q;
     a.n_ctx = n_ctx;
     a.dbg = g_enc_attn_dbg;
     {
@@ -517,7 +519,7 @@ int launch_encoder_attention(const float *d_q, const float *d_k, const float *d_
     }
     a.scale_log2 = (float)(0.125 * 1.4426950408889634);  // Dh^-1/2 (= (Dh^-1/4)^2 of upstream) * log2(e)
     WCA_CUDA(cudaFuncSetAttribute(ea::enc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ea::kSmemBytes));
-    const dim3 grid((unsigned)((n_ctx + ea::kQRows - 1) / ea::kQRows), (unsigned)n_heads, (unsigned)n_batch);
+    const dim3 grid((unsigned)((n_q + ea::kQRows - 1) / ea::kQRows), (unsigned)n_heads, (unsigned)n_batch);
     ea::enc_attn_kernel<<<grid, ea::kThreads, ea::kSmemBytes, stream>>>(maps, a);
     WCA_LAUNCH_CHECK("enc_attn_kernel");
     return WCA_OK;

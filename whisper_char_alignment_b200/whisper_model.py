@@ -55,8 +55,8 @@ def dims_for(name: str) -> ModelDimensions:
     return ModelDimensions(*SIZES[name])
 
 
-#: "wca": the encoder's non-causal self-attention runs on csrc/enc_attn.cu; "sdpa": torch SDPA (fp32 CUDA-core
-#: kernel).  Decoder self/cross attention (a few dozen tokens) always stays on SDPA.
+#: "wca": unmasked attention (encoder self-attention, decoder cross-attention output) runs on csrc/enc_attn.cu;
+#: "sdpa": torch SDPA (fp32 CUDA-core kernel).  The decoder's causal self-attention always stays on SDPA.
 ENCODER_ATTENTION = os.environ.get("WCA_ENCODER_ATTENTION", "wca")
 
 
@@ -94,13 +94,14 @@ class Attention(nn.Module):
     def forward(self, x, xa=None, causal: bool = False):
         src = x if xa is None else xa
         q, k, v = self.query(x), self.key(src), self.value(src)
-        if (xa is None and not causal and ENCODER_ATTENTION == "wca" and q.is_cuda and q.dtype == torch.float32
+        if (not causal and ENCODER_ATTENTION == "wca" and q.is_cuda and q.dtype == torch.float32
                 and q.shape[-1] == 64 * self.n_head):
-            # encoder self-attention: the sm_100a tcgen05 kernel (csrc/enc_attn.cu) reads the projection
-            # outputs in place (no head split / transposes) and keeps fp32 accuracy with 3 x tf32 products
+            # unmasked attention (encoder self-attention, decoder cross-attention output): the sm_100a
+            # tcgen05 kernel (csrc/enc_attn.cu) reads the projection outputs in place (no head split /
+            # transposes) and keeps fp32 accuracy with 3 x tf32 products
             from . import _cabi
 
-            return self.out(_cabi.encoder_attention(q, k, v, self.n_head)), None
+            return self.out(_cabi.full_attention(q, k, v, self.n_head)), None
         q, k, v = self._split(q), self._split(k), self._split(v)
         # SDPA's default scale is d_head^-1/2 == (d_head^-1/4)^2, the published scaling
         ctx = F.scaled_dot_product_attention(q, k, v, is_causal=causal and q.shape[2] > 1)
@@ -140,8 +141,23 @@ class AudioEncoder(nn.Module):
         self.blocks = nn.ModuleList([Block(width, heads, cross=False) for _ in range(layers)])
         self.ln_post = _Norm(width)
 
+    def _conv2_as_gemm(self, x):
+        """conv2 (kernel 3, stride 2, padding 1) as ONE cuBLAS GEMM over unfolded windows: same sums in
+        another order, output already in the (batch, frames, width) layout the blocks want.  cuDNN's
+        fp32 path for this shape is a CUDA-core kernel (3% of a step) and hands back (batch, width,
+        frames), which made every LayerNorm of the encoder copy a permuted residual stream."""
+        b, c, _ = x.shape
+        cols = F.pad(x, (1, 1)).unfold(2, 3, 2)                      # (b, c, frames_out, 3) view
+        cols = cols.permute(0, 2, 1, 3).reshape(b * cols.shape[2], c * 3)
+        w = self.conv2.weight.to(x.dtype).reshape(self.conv2.out_channels, c * 3)
+        return torch.addmm(self.conv2.bias.to(x.dtype), cols, w.t()).view(b, -1, self.conv2.out_channels)
+
     def forward(self, mel):
-        x = F.gelu(self.conv2(F.gelu(self.conv1(mel)))).transpose(1, 2)
+        x = F.gelu(self.conv1(mel))
+        if x.is_cuda and x.dtype == torch.float32:
+            x = F.gelu(self._conv2_as_gemm(x))
+        else:
+            x = F.gelu(self.conv2(x)).transpose(1, 2).contiguous()
         if x.shape[1:] != self.positional_embedding.shape:
             raise ValueError(f"incorrect audio shape {tuple(mel.shape)}: expected {2 * self.positional_embedding.shape[0]} frames")
         x = (x + self.positional_embedding).to(x.dtype)
