@@ -89,19 +89,24 @@ def parse():
     ap.add_argument("--workload", default="timit", choices=["timit", "librispeech", "ami", "probe"])
     ap.add_argument("--batch", type=int, default=16, help="utterances per step per GPU")
     ap.add_argument("--topk", type=int, default=10)
+    ap.add_argument("--aggr", default=None, choices=["topk", "mean"], help="default: topk (mean for the ami workload)")
     ap.add_argument("--medfilt_width", type=int, default=3)
     ap.add_argument("--fp32-gemm", default="bf16x9", choices=["bf16x9", "native"],
                     help="cuBLAS fp32 GEMMs of the upstream linears: BF16x9-emulated fp32 (cuBLAS 12.9) or SIMT SGEMM")
     ap.add_argument("--profile-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed `value` region (for `ncu --profile-from-start off`)")
     ap.add_argument("--cpu-sample", type=int, default=2, help="utterances timed for cpu_baseline (0 = skip)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.aggr is None:
+        args.aggr = "mean" if args.workload == "ami" else "topk"
+    return args
 
 
 def workload_config(args, world):
     return {
-        "workload": f"{args.workload}-shaped synthetic, Whisper-{args.model} dims (random-init, seeded), char units, "
-                    f"aggr=topk k={args.topk}, medfilt_width={args.medfilt_width}",
+        "workload": f"{args.workload}-shaped synthetic, Whisper-{args.model} dims (random-init, seeded), "
+                    f"{'subword' if args.workload == 'ami' else 'char'} units, "
+                    f"aggr={args.aggr}" + (f" k={args.topk}" if args.aggr == "topk" else "") + f", medfilt_width={args.medfilt_width}",
         "utterances_per_step_per_gpu": args.batch,
         "global_batch": args.batch * world,
         "parallelism": f"utterance sharding x{world}, no data-path collective; one final all_gather",
@@ -200,7 +205,7 @@ def cpu_reference_run(args, n_utts, warm):
     def one(u):
         w, _ = ref_path.get_attentions(u.mel, u.tokens, om, tk, u.max_frames, args.medfilt_width, 1.0)
         return ref_path.force_align(w, u.text_tokens, tk, "char" if args.workload != "ami" else "subword",
-                                    "topk", args.topk)
+                                    args.aggr, args.topk)
 
     for u in utts[:warm]:
         one(u)
@@ -272,7 +277,7 @@ def main():
     def align(mels, toks, batch):
         ws, _ = timing.get_attentions_batch(mels, toks, model, tk, [u.max_frames for u in batch],
                                             args.medfilt_width, 1.0)
-        return timing.force_align_batch(ws, [u.text_tokens for u in batch], tk, unit, "topk", args.topk)
+        return timing.force_align_batch(ws, [u.text_tokens for u in batch], tk, unit, args.aggr, args.topk)
 
     def step_resident(i):
         mels, toks = resident[i % n_batches]
@@ -348,7 +353,7 @@ def main():
     sot = len(tk.sot_sequence)
     for u in b0:
         n_rows = len(u.tokens) - sot - 1
-        d2h += n_rows * u.max_frames * 4 + 2 * 8 * (len(u.text.split()) + 1) + 2 * 4 * args.topk
+        d2h += n_rows * u.max_frames * 4 + 2 * 8 * (len(u.text.split()) + 1) + (2 * 4 * args.topk if args.aggr == "topk" else 0)
 
     # ---- roofline of the dominant kernel of OUR path: the capture launch --------------------
     L, H, d = dims.n_text_layer, dims.n_text_head, dims.n_text_state
