@@ -87,7 +87,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="medium")
     ap.add_argument("--workload", default="timit", choices=["timit", "librispeech", "ami", "probe"])
-    ap.add_argument("--batch", type=int, default=16, help="utterances per step per GPU")
+    ap.add_argument("--batch", type=int, default=32, help="utterances per step per GPU")
     ap.add_argument("--topk", type=int, default=10)
     ap.add_argument("--aggr", default=None, choices=["topk", "mean"], help="default: topk (mean for the ami workload)")
     ap.add_argument("--medfilt_width", type=int, default=3)
@@ -110,7 +110,7 @@ def workload_config(args, world):
         "utterances_per_step_per_gpu": args.batch,
         "global_batch": args.batch * world,
         "parallelism": f"utterance sharding x{world}, no data-path collective; one final all_gather",
-        "cache": "inputs larger than L2: each step streams the 3 GB fp32 weights and >1 GB of activations",
+        "cache": "inputs larger than L2: each step streams the 3 GB fp32 weights and >2 GB of activations",
         "fp32_gemm": ("cuBLAS 12.9 BF16x9-emulated fp32 (CUBLAS_EMULATE_SINGLE_PRECISION=1) for the upstream linears"
                       if FP32_GEMM == "bf16x9" else "cuBLAS SIMT SGEMM (allow_tf32 off)"),
     }

@@ -46,7 +46,7 @@ bool capture_tc_supported(int max_tokens, int max_frames, int medfilt_width);
 int read_capture_trace(long long *, int);
 int launch_medfilt_softmax_rows(const float *, int64_t, int64_t, int, int, float, float *, int, cudaStream_t);
 int launch_medfilt_softmax_batched(float *, const wca_utt_t *, int, int, int, int, int, float, int, cudaStream_t);
-int launch_head_scores(const float *, const wca_utt_t *, int, int, float, float, float, float *, cudaStream_t);
+int launch_head_scores(const float *, const wca_utt_t *, int, int, int, float, float, float, float *, cudaStream_t);
 int launch_topk_heads(const float *, const wca_utt_t *, int, int, int32_t *, float *, cudaStream_t);
 int launch_aggregate_heads(const float *, const int32_t *, const wca_utt_t *, int, int, int, float *, cudaStream_t);
 int64_t dtw_workspace_bytes(int, int, int);
@@ -181,12 +181,12 @@ int wca_head_scores(const float *d_ws, const wca_utt_t *d_utts, int n_utts, int 
                     int max_frames, float w_colnorm, float w_rownorm, float w_coverage, float *d_scores,
                     wca_stream_t stream) {
     (void)max_tokens;
-    (void)max_frames;
     WCA_CHECK_ARG(d_ws && d_utts && d_scores, "wca_head_scores: null pointer");
+    WCA_CHECK_ARG(max_frames >= 1, "wca_head_scores: max_frames=%d", max_frames);
     WCA_CHECK_ARG(n_heads >= 1 && n_heads <= 65535 * 32 && n_utts >= 0 && n_utts <= 65535,
                   "wca_head_scores: bad geometry (%d heads, %d utts)", n_heads, n_utts);
     if (n_utts == 0) return WCA_OK;
-    return launch_head_scores(d_ws, d_utts, n_utts, n_heads, w_colnorm, w_rownorm, w_coverage, d_scores,
+    return launch_head_scores(d_ws, d_utts, n_utts, n_heads, max_frames, w_colnorm, w_rownorm, w_coverage, d_scores,
                               static_cast<cudaStream_t>(stream));
 }
 
