@@ -9,9 +9,11 @@
 // barrier, and a 128-thread CTA runs four independent problems, so a batch of small
 // problems (BASELINE config 2: 41 x 150; config 5: 384 heads per utterance) fills the SMs
 // with independent dependency chains.  The cost matrix is first staged into shared memory
-// with coalesced loads (negated on the way) whenever it fits next to the trace, so no global
-// load sits on the step-to-step dependency chain; larger problems read their columns
-// directly.  The trace is 2 bits per cell, packed per (column, lane) word and kept in shared
+// with coalesced 16-byte loads whenever it fits next to the trace, so no global load sits on the
+// step-to-step dependency chain; larger problems (LibriSpeech-shaped, 401 x 1500) prefetch each
+// lane's strip of a column kPrefetch steps ahead with cp.async into a small per-lane ring in shared
+// memory (a column step is ~250 cycles, an L2 round trip ~1400: one column of lookahead left the
+// sweep latency-bound).  The trace is 2 bits per cell, packed per (column, lane) word and kept in shared
 // memory (global workspace only when a problem does not fit); lane 0 backtraces on the device
 // and only N jump frames / W word times leave the SM.
 //
@@ -44,9 +46,21 @@ struct DtwLaunch {
     int64_t trace_stride;      // bytes of trace per problem (shared or global)
     int jump_stride;           // ints of jump buffer per problem in shared memory
     int trace_in_smem;
-    int stage_floats;          // floats of staged cost matrix per problem in shared memory (0: read global)
+    int staged;                // 1: the whole cost matrix of a problem is staged in shared memory
+    int ring;                  // 1: (not staged) each lane prefetches its strip through a cp.async ring in shared memory
+    int xs_floats;             // floats of the staged matrix / the ring per problem in shared memory
     int warps;                 // problems per CTA
 };
+
+constexpr int kPrefetch = 8;  // ring slots = columns in flight per lane
+
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
 template <int R>
 __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
@@ -65,7 +79,7 @@ __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
     Word *trace = p.trace_in_smem ? reinterpret_cast<Word *>(after_jump + (size_t)warp * p.trace_stride)
                                   : reinterpret_cast<Word *>(p.trace_ws + (size_t)prob * p.trace_stride);
     float *xs = reinterpret_cast<float *>(after_jump + (p.trace_in_smem ? (size_t)p.warps * p.trace_stride : 0)) +
-                (size_t)warp * p.stage_floats;
+                (size_t)warp * p.xs_floats;
     if (N <= 0 || M <= 0) {
         if (lane == 0 && p.path_len) p.path_len[prob] = 0;
         return;
@@ -74,14 +88,24 @@ __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
 
     // ---- stage the cost matrix (coalesced, sign applied once) -----------------------------------
     const float *xg = p.matrix + u.matrix_off;
-    const bool staged = p.stage_floats > 0;
+    const bool staged = p.staged != 0;
     if (staged) {
+        // same misalignment in shared memory as in global memory, so the body moves 16 bytes per lane and load
         const int total = N * M;
+        const int mis = (int)(((uintptr_t)xg >> 2) & 3);
+        xs += mis;
+        const int head = min(total, (4 - mis) & 3);
+        const int body = (total - head) >> 2;
+        if (lane < head) xs[lane] = p.negate ? -ld_stream(xg + lane) : ld_stream(xg + lane);
+        const float4 *g4 = reinterpret_cast<const float4 *>(xg + head);
+        float4 *s4 = reinterpret_cast<float4 *>(xs + head);
 #pragma unroll 8
-        for (int e = lane; e < total; e += 32) {  // independent loads: eight rows of requests in flight per lane
-            const float v = ld_stream(xg + e);
-            xs[e] = p.negate ? -v : v;
+        for (int e = lane; e < body; e += 32) {  // independent loads: 4 KB of requests in flight per warp
+            float4 v = ld_stream4(g4 + e);
+            if (p.negate) v = make_float4(-v.x, -v.y, -v.z, -v.w);
+            s4[e] = v;
         }
+        for (int e = head + 4 * body + lane; e < total; e += 32) xs[e] = p.negate ? -ld_stream(xg + e) : ld_stream(xg + e);
         __syncwarp();
     }
     const float *x = staged ? xs : xg;
@@ -94,16 +118,45 @@ __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
     for (int r = 0; r < R; ++r) left[r] = INFINITY;
     float diag_top = (lane == 0) ? 0.f : INFINITY;  // cost[row above strip][j-1]; cost[0][0] = 0 for lane 0
     float xn[R];
-    auto load_col = [&](int j, float (&dst)[R]) {  // x[row][j-1] for the strip, 0 outside
+    // Ring mode: slot (step % kPrefetch) of this lane holds x[strip rows][column consumed at that step]
+    const bool ring_mode = !staged && p.ring;
+    float *ring = xs;  // [kPrefetch][R][32 lanes] floats (the staged-matrix slice is unused in this mode)
+    auto prefetch_col = [&](int step) {  // column this lane consumes at `step`: j = step - lane + 1
+        const int j = step - lane + 1;
+        if (j >= 1 && j <= M) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int row = row0 + r;
+                if (row < N) cp_async4(&ring[((step % kPrefetch) * R + r) * 32 + lane], xg + (int64_t)row * M + (j - 1));
+            }
+        }
+        cp_async_commit();
+    };
+    auto load_col = [&](int j, float (&dst)[R]) {  // x[row][j-1] for the strip, 0 outside (sign applied at use)
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int row = row0 + r;
             float v = 0.f;
             if (row < N && j >= 1 && j <= M) v = x[(int64_t)row * M + (j - 1)];
-            dst[r] = flip ? -v : v;
+            dst[r] = v;
         }
     };
-    load_col(1 - lane, xn);
+    auto take_col = [&](int step, float (&dst)[R]) {  // the ring slot of `step`, once its group has landed
+        const int j = step - lane + 1;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float v = 0.f;
+            if (row0 + r < N && j >= 1 && j <= M) v = ring[((step % kPrefetch) * R + r) * 32 + lane];
+            dst[r] = v;
+        }
+    };
+    if (ring_mode) {
+        for (int t = 0; t < kPrefetch; ++t) prefetch_col(t);
+        cp_async_wait<kPrefetch - 1>();  // group of step 0 has landed
+        take_col(0, xn);
+    } else {
+        load_col(1 - lane, xn);
+    }
     const int n_steps = M + 31;
     for (int s = 0; s < n_steps; ++s) {
         const int j = s - lane + 1;
@@ -112,8 +165,15 @@ __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
         if (lane == 0) up_top = INFINITY;  // cost[0][j], j >= 1
         float xc[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) xc[r] = xn[r];
-        load_col(j + 1, xn);  // next column in flight while this one is computed
+        for (int r = 0; r < R; ++r) xc[r] = flip ? -xn[r] : xn[r];
+        if (ring_mode) {
+            // slot of step s has been consumed into xc: refill it for step s + kPrefetch, then wait for step s + 1
+            prefetch_col(s + kPrefetch);
+            cp_async_wait<kPrefetch - 1>();
+            take_col(s + 1, xn);
+        } else {
+            load_col(j + 1, xn);  // next column in flight while this one is computed
+        }
         if (j >= 1 && j <= M) {
             Word tw = 0;
             float c0 = diag_top;  // cost[i-1][j-1]
@@ -121,18 +181,11 @@ __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const float c2 = left[r];  // cost[i][j-1]
-                float c;
-                uint32_t code;
-                if (c0 < c1 && c0 < c2) {
-                    c = c0;
-                    code = 0u;
-                } else if (c1 < c0 && c1 < c2) {
-                    c = c1;
-                    code = 1u;
-                } else {
-                    c = c2;
-                    code = 2u;
-                }
+                // selects, not branches: the lanes of a warp take different cases in every cell
+                const bool d0 = (c0 < c1) & (c0 < c2);
+                const bool d1 = (c1 < c0) & (c1 < c2);
+                const float c = d0 ? c0 : (d1 ? c1 : c2);
+                const uint32_t code = d0 ? 0u : (d1 ? 1u : 2u);
                 const float cost = __fadd_rn(xc[r], c);
                 tw |= (Word)((Word)code << (2 * (r % (4 * (int)sizeof(Word)))));
                 c0 = c2;    // this row's old value is the next row's diagonal
@@ -194,6 +247,184 @@ __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
     }
 }
 
+// ---- several warps per problem (long texts: LibriSpeech-shaped 401 x 1500) -------------------------
+// One CTA = one problem, WPP warps, global lane g = warp * 32 + lane owns R consecutive rows.  A single
+// warp with R = 16 is bound by its own dependency chain (16 cells per step, ~100 cycles each); with
+// 128 lanes of R = 4 the step is 4 cells and the sweep has M + 127 steps.  Inside a warp the strip above
+// arrives by __shfl_up as before; between warps lane 31 of warp w publishes the bottom row of its strip,
+// column by column, in a shared line `edge[w][j]` followed by a progress counter, and lane 0 of warp w + 1
+// (which runs 32 steps behind by construction) polls the counter: no block barrier on the recurrence.
+template <int R, int WPP>
+__global__ void __launch_bounds__(32 * WPP) dtw_align_multi_kernel(const DtwLaunch p) {
+    using Word = typename TraceWord<R>::type;
+    constexpr int L = 32 * WPP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = threadIdx.x;
+    const int prob = blockIdx.x;
+    const wca_utt_t u = p.utts[prob];
+    const int N = u.row_end - u.row_begin;
+    const int M = u.n_frames;
+    // shared memory: [64 bytes spare][jump buffer][edge lines][trace]
+    int32_t *jump_s = reinterpret_cast<int32_t *>(smem_raw + 64);
+    // [WPP - 1][edge_stride] of {cost bits, column tag}: value and flag travel in ONE 8-byte store, so the
+    // producer needs no fence and the consumer polls the very word it wants (tag 0 = not yet written)
+    unsigned long long *edge = reinterpret_cast<unsigned long long *>(smem_raw + 64 + (size_t)p.jump_stride * 4);
+    const int edge_stride = (int)(p.xs_floats / 2 / (WPP > 1 ? WPP - 1 : 1));
+    Word *trace = p.trace_in_smem
+                      ? reinterpret_cast<Word *>(smem_raw + 64 + (size_t)p.jump_stride * 4 + (size_t)p.xs_floats * 4)
+                      : reinterpret_cast<Word *>(p.trace_ws + (size_t)prob * p.trace_stride);
+    if (N <= 0 || M <= 0) {
+        if (g == 0 && p.path_len) p.path_len[prob] = 0;
+        return;
+    }
+    for (int r = g; r < N; r += L) jump_s[r] = -1;
+    for (int e = g; e < (WPP - 1) * edge_stride; e += L) edge[e] = 0ull;
+    __syncthreads();
+
+    const bool flip = p.negate != 0;
+    const int row0 = g * R;
+    float left[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) left[r] = INFINITY;
+    float diag_top = (g == 0) ? 0.f : INFINITY;
+    const float *xg = p.matrix + u.matrix_off;
+    auto load_col = [&](int j, float (&dst)[R]) {  // x[row][j-1] for the strip, 0 outside
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int row = row0 + r;
+            float v = 0.f;
+            if (row < N && j >= 1 && j <= M) v = xg[(int64_t)row * M + (j - 1)];  // L1-cached: 8 steps share a sector
+            dst[r] = v;  // the sign is applied where the value is consumed: touching it here would wait for the load
+        }
+    };
+    // kAhead columns of lookahead in registers (ncu: 40 % of the stall samples were long-scoreboard waits on the
+    // cost loads); the step loop is unrolled by kAhead so that the ring index is a compile-time constant.
+    constexpr int kAhead = 8;
+    float xq[kAhead][R];
+#pragma unroll
+    for (int d = 0; d < kAhead; ++d) load_col(d + 1 - lane, xq[d]);
+    const int n_steps = M + 31;  // local steps of this warp; column of a lane: j = s - lane + 1
+    const volatile unsigned long long *edge_in = edge + (size_t)(warp > 0 ? warp - 1 : 0) * edge_stride;
+    volatile unsigned long long *edge_out = edge + (size_t)(warp < WPP - 1 ? warp : 0) * edge_stride;
+    for (int s0 = 0; s0 < n_steps; s0 += kAhead) {
+#pragma unroll
+      for (int d = 0; d < kAhead; ++d) {
+        const int s = s0 + d;
+        const int j = s - lane + 1;
+        float up_top = __shfl_up_sync(0xffffffffu, left[R - 1], 1);
+        if (lane == 0) {
+            up_top = INFINITY;  // cost[0][j], j >= 1 (first warp)
+            if (warp > 0 && j <= M) {
+                // bottom row of the strip above (last lane of the previous warp), column j
+                unsigned long long w;
+                do {
+                    w = edge_in[j - 1];
+                } while ((uint32_t)(w >> 32) != (uint32_t)j);
+                up_top = __uint_as_float((uint32_t)w);
+            }
+        }
+        float xc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) xc[r] = flip ? -xq[d][r] : xq[d][r];
+        load_col(j + kAhead, xq[d]);
+        if (j >= 1 && j <= M) {
+            Word tw = 0;
+            float c0 = diag_top;
+            float c1 = up_top;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float c2 = left[r];
+                // selects, not branches: the lanes of a warp take different cases in every cell
+                const bool d0 = (c0 < c1) & (c0 < c2);
+                const bool d1 = (c1 < c0) & (c1 < c2);
+                const float c = d0 ? c0 : (d1 ? c1 : c2);
+                const uint32_t code = d0 ? 0u : (d1 ? 1u : 2u);
+                const float cost = __fadd_rn(xc[r], c);
+                tw |= (Word)((Word)code << (2 * (r % (4 * (int)sizeof(Word)))));
+                c0 = c2;
+                c1 = cost;
+                left[r] = cost;
+            }
+            diag_top = up_top;
+            trace[(int64_t)(j - 1) * L + g] = tw;
+            if (lane == 31 && warp < WPP - 1)
+                edge_out[j - 1] = ((unsigned long long)(uint32_t)j << 32) | __float_as_uint(left[R - 1]);
+        }
+      }
+    }
+    __syncthreads();
+
+    if (g == 0) {
+        const int cap = N + M;
+        int32_t *pt = p.path_text ? p.path_text + u.path_off : nullptr;
+        int32_t *pj = p.path_time ? p.path_time + u.path_off : nullptr;
+        int bi = N, bj = M, pos = cap;
+        while (bi > 0 || bj > 0) {
+            --pos;
+            if (pt) {
+                pt[pos] = bi - 1;
+                pj[pos] = bj - 1;
+            }
+            uint32_t code;
+            if (bj == 0) code = 1u;
+            else if (bi == 0) code = 2u;
+            else {
+                const int row = bi - 1;
+                const Word w = trace[(int64_t)(bj - 1) * L + row / R];
+                code = (uint32_t)(w >> (2 * (row % R))) & 3u;
+            }
+            if (code != 2u && bi >= 1) jump_s[bi - 1] = bj - 1;
+            if (code == 0u) {
+                --bi;
+                --bj;
+            } else if (code == 1u) {
+                --bi;
+            } else {
+                --bj;
+            }
+        }
+        if (p.path_len) p.path_len[prob] = cap - pos;
+    }
+    __syncthreads();
+
+    if (p.jump_frames)
+        for (int r = g; r < N; r += L) p.jump_frames[u.jump_off + r] = jump_s[r];
+    if (p.word_bounds && p.start_times && p.end_times) {
+        const int32_t *wb = p.word_bounds + u.word_off;
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        for (int w = g; w < u.n_words; w += L) {
+            const int a = wb[w], b = wb[w + 1];
+            p.start_times[u.word_off + w] = (a >= 0 && a < N) ? (double)jump_s[a] / WCA_TOKENS_PER_SECOND : nan;
+            p.end_times[u.word_off + w] = (b >= 0 && b < N) ? (double)jump_s[b] / WCA_TOKENS_PER_SECOND : nan;
+        }
+    }
+}
+
+// Geometry of the multi-warp variant for a launch (0 warps: use the warp-per-problem kernel).
+struct MultiPlan {
+    int wpp, r;
+    size_t trace, edge, smem;
+    int trace_in_smem;
+};
+static MultiPlan dtw_multi_plan(int max_rows, int max_frames) {
+    MultiPlan m = {0, 0, 0, 0, 0, 0};
+    if (max_rows <= 128 || max_rows > 1024) return m;
+    m.wpp = max_rows <= 512 ? 4 : 8;
+    const int lanes = 32 * m.wpp;
+    m.r = (max_rows + lanes - 1) / lanes <= 2 ? 2 : 4;
+    const size_t word = 1;  // R <= 4: one byte per (column, lane)
+    m.trace = (((size_t)max_frames * lanes * word) + 15) & ~(size_t)15;
+    m.edge = (size_t)(m.wpp - 1) * (((size_t)max_frames + 3) & ~(size_t)3) * 8;
+    const size_t jump = (size_t)((max_rows + 3) & ~3) * 4;
+    m.smem = 64 + jump + m.edge + m.trace;
+    m.trace_in_smem = 1;
+    if (m.smem > 227u * 1024u) {
+        m.smem = 64 + jump + m.edge;
+        m.trace_in_smem = 0;
+    }
+    return m;
+}
+
 static int strip_rows(int max_rows) {
     int r = 1;
     while (r * 32 < max_rows) r *= 2;
@@ -206,35 +437,53 @@ static size_t dtw_trace_bytes(int max_rows, int max_frames) {
 }
 constexpr size_t kSmemBudget = 227u * 1024u;
 
-// Shared-memory plan for a launch: problems per CTA, whether the trace and the staged matrix fit.
+// Shared-memory plan for a launch: problems per CTA, whether the trace, the staged matrix or the prefetch ring fit.
 struct DtwPlan {
-    int warps, trace_in_smem, stage_floats;
+    int warps, trace_in_smem, staged, ring, xs_floats;
     size_t smem;
 };
 static DtwPlan dtw_plan(int max_rows, int max_frames) {
     const size_t jump = (size_t)((max_rows + 3) & ~3) * 4;
     const size_t trace = dtw_trace_bytes(max_rows, max_frames);
-    const size_t stage = (((size_t)max_rows * max_frames + 3) & ~(size_t)3) * 4;
+    const size_t stage = (((size_t)max_rows * max_frames + 3 + 3) & ~(size_t)3) * 4;  // + slack for the alignment shift
+    const size_t ring = (size_t)kPrefetch * strip_rows(max_rows) * 32 * 4;
     DtwPlan pl;
     for (int warps = 4; warps >= 1; warps >>= 1) {  // prefer everything on chip, then more problems per CTA
         if (warps * (jump + trace + stage) <= kSmemBudget) {
-            pl = {warps, 1, (int)(stage / 4), warps * (jump + trace + stage)};
+            pl = {warps, 1, 1, 0, (int)(stage / 4), warps * (jump + trace + stage)};
+            return pl;
+        }
+    }
+    for (int warps = 4; warps >= 1; warps >>= 1) {
+        if (warps * (jump + trace + ring) <= kSmemBudget) {
+            pl = {warps, 1, 0, 1, (int)(ring / 4), warps * (jump + trace + ring)};
             return pl;
         }
     }
     for (int warps = 4; warps >= 1; warps >>= 1) {
         if (warps * (jump + trace) <= kSmemBudget) {
-            pl = {warps, 1, 0, warps * (jump + trace)};
+            pl = {warps, 1, 0, 0, 0, warps * (jump + trace)};
             return pl;
         }
     }
-    pl = {4, 0, 0, 4 * jump};
+    pl = {4, 0, 0, 1, (int)(ring / 4), 4 * (jump + ring)};  // trace in the global workspace
     return pl;
 }
 
 int64_t dtw_workspace_bytes(int n_utts, int max_rows, int max_frames) {
+    const MultiPlan m = dtw_multi_plan(max_rows, max_frames);
+    if (m.wpp) return m.trace_in_smem ? 0 : (int64_t)n_utts * (int64_t)m.trace;
     if (dtw_plan(max_rows, max_frames).trace_in_smem) return 0;
     return (int64_t)n_utts * (int64_t)dtw_trace_bytes(max_rows, max_frames);
+}
+
+template <int R, int WPP>
+static int launch_multi(const DtwLaunch &p, size_t smem, cudaStream_t stream) {
+    if (smem > 48u * 1024u)
+        WCA_CUDA(cudaFuncSetAttribute(dtw_align_multi_kernel<R, WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dtw_align_multi_kernel<R, WPP><<<p.n_utts, 32 * WPP, smem, stream>>>(p);
+    WCA_LAUNCH_CHECK("dtw_align_multi_kernel");
+    return WCA_OK;
 }
 
 template <int R>
@@ -270,11 +519,33 @@ int launch_dtw_align(const float *d_matrix, const wca_utt_t *d_utts, int n_utts,
     p.start_times = d_start_times;
     p.end_times = d_end_times;
     p.trace_ws = nullptr;
-    p.trace_stride = (int64_t)dtw_trace_bytes(max_rows, max_frames);
     p.jump_stride = (max_rows + 3) & ~3;
+    const MultiPlan mp = dtw_multi_plan(max_rows, max_frames);
+    if (mp.wpp && ((uintptr_t)d_matrix & 15) == 0) {  // long texts: several warps per problem (16-byte group loads)
+        p.trace_stride = (int64_t)mp.trace;
+        p.trace_in_smem = mp.trace_in_smem;
+        p.staged = 0;
+        p.ring = 0;
+        p.xs_floats = (int)(mp.edge / 4);
+        p.warps = 1;
+        if (!p.trace_in_smem) {
+            const int64_t need = (int64_t)n_utts * p.trace_stride;
+            if (!d_trace_ws || trace_ws_bytes < need) {
+                set_error("wca_dtw_align: trace workspace of %lld bytes required, %lld given", (long long)need,
+                          (long long)trace_ws_bytes);
+                return WCA_ERR_INVALID;
+            }
+            p.trace_ws = static_cast<unsigned char *>(d_trace_ws);
+        }
+        if (mp.wpp == 4) return mp.r == 2 ? launch_multi<2, 4>(p, mp.smem, stream) : launch_multi<4, 4>(p, mp.smem, stream);
+        return mp.r == 2 ? launch_multi<2, 8>(p, mp.smem, stream) : launch_multi<4, 8>(p, mp.smem, stream);
+    }
+    p.trace_stride = (int64_t)dtw_trace_bytes(max_rows, max_frames);
     const DtwPlan pl = dtw_plan(max_rows, max_frames);
     p.trace_in_smem = pl.trace_in_smem;
-    p.stage_floats = pl.stage_floats;
+    p.staged = pl.staged;
+    p.ring = pl.ring;
+    p.xs_floats = pl.xs_floats;
     p.warps = pl.warps;
     const size_t smem = pl.smem;
     if (!p.trace_in_smem) {
