@@ -1,4 +1,5 @@
 #!/bin/bash
+# Round-end check on one B200: GPU suite, ncu capture of the capture launch inside bench.py (-> tools/ncu_traffic.py), bench, reference arm.
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/t_native.log 2>&1; echo "tests native rc=$?"; tail -3 gpurun_out/t_native.log
 python bench.py --steps 1 --warmup 3 --cpu-sample 0 > /dev/null 2>&1; echo "plain rc=$?"
