@@ -149,3 +149,19 @@ def test_product_never_imports_the_oracle():
                 assert "import oracle" not in text and "from oracle" not in text, f
     code = "import sys; import whisper_char_alignment_b200; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
     subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)
+
+
+def test_greedy_decode_runs_on_cpu_and_stops_at_eot(tokenizer):
+    """whisper.decode stand-in (infer_ali.py:60): text tokens only, batch == single, eot never returned."""
+    import torch
+
+    from whisper_char_alignment_b200 import whisper_model
+
+    model = whisper_model.random_init(whisper_model.ModelDimensions(80, 32, 64, 1, 1, 51865, 32, 64, 1, 1))
+    g = torch.Generator().manual_seed(0)
+    mel = torch.randn(2, 80, 64, generator=g)
+    both = whisper_model.greedy_decode(model, mel, tokenizer, max_tokens=6)
+    one = whisper_model.greedy_decode(model, mel[0], tokenizer, max_tokens=6)
+    assert len(both) == 2 and both[0] == one
+    for toks in both:
+        assert len(toks) <= 6 and all(0 <= t < tokenizer.eot for t in toks)

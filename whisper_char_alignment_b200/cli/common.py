@@ -42,12 +42,18 @@ def load_model_and_tokenizer(name: str, device, qk_gain: float = 4.0):
         return model, byte_tokenizer(model.is_multilingual, language="English"), None
 
 
-def transcribe(whisper_pkg, model, mel, reference_text: str) -> str:
-    """The reference transcribes with whisper.decode (infer_ali.py:60); that autoregressive step is
-    upstream and out of scope, so offline the reference transcript is force-aligned instead."""
-    if whisper_pkg is None:
-        return reference_text
-    return whisper_pkg.decode(model, mel, whisper_pkg.DecodingOptions(language="en")).text
+TRANSCRIBE = os.environ.get("WCA_TRANSCRIBE", "reference")  # offline default: align the reference transcript
+
+
+def transcribe(whisper_pkg, model, mel, reference_text: str, tokenizer=None) -> str:
+    """The reference transcribes with whisper.decode (infer_ali.py:60).  With openai-whisper installed
+    that call is used as is; offline the reference transcript is force-aligned (a random-init model
+    transcribes noise), or, with WCA_TRANSCRIBE=greedy and a checkpoint, the built-in greedy decoder."""
+    if whisper_pkg is not None:
+        return whisper_pkg.decode(model, mel, whisper_pkg.DecodingOptions(language="en")).text
+    if TRANSCRIBE == "greedy" and tokenizer is not None:
+        return tokenizer.decode(whisper_model.greedy_decode(model, mel, tokenizer))
+    return reference_text
 
 
 def prepare(record, tokenizer, unit, device, whisper_pkg, model):
@@ -56,7 +62,7 @@ def prepare(record, tokenizer, unit, device, whisper_pkg, model):
     _, mel, duration, text, starts, ends, fid = record
     mel = mel.to(device)
     text = remove_punctuation(text)
-    transcription = remove_punctuation(transcribe(whisper_pkg, model, mel, text)) or " "
+    transcription = remove_punctuation(transcribe(whisper_pkg, model, mel, text, tokenizer)) or " "
     text_tokens = encode(transcription, tokenizer, unit)
     tokens = torch.tensor([*tokenizer.sot_sequence, tokenizer.no_timestamps, *text_tokens, tokenizer.eot], device=device)
     max_frames = int(duration) // AUDIO_SAMPLES_PER_TOKEN

@@ -248,5 +248,36 @@ def random_init(dims: ModelDimensions, seed: int = 0, qk_gain: float = 1.0) -> W
     return model.eval()
 
 
+@torch.no_grad()
+def greedy_decode(model: Whisper, mel: torch.Tensor, tokenizer, max_tokens: int = 224) -> list:
+    """Greedy transcription without timestamps -- what the reference obtains from
+    `whisper.decode(model, mel, DecodingOptions(language="en"))` (infer_ali.py:60) for the text it then
+    aligns.  mel: (n_mels, 3000) or (B, n_mels, 3000).  Returns one list of text tokens per utterance.
+    The prefix is re-run every step (no KV cache): the decoder context is at most 448 tokens and this
+    step is outside the alignment hot path."""
+    single = mel.dim() == 2
+    if single:
+        mel = mel.unsqueeze(0)
+    xa = model.encoder(mel)
+    b = mel.shape[0]
+    prefix = [*tokenizer.sot_sequence, tokenizer.no_timestamps]
+    tokens = torch.tensor([prefix] * b, device=mel.device)
+    done = torch.zeros(b, dtype=torch.bool, device=mel.device)
+    limit = min(max_tokens, model.dims.n_text_ctx - len(prefix) - 1)
+    for _ in range(limit):
+        logits = model.decoder(tokens, xa)[:, -1]
+        logits[:, tokenizer.eot + 1:] = -float("inf")  # no special tokens / timestamps in the text
+        nxt = logits.argmax(-1)
+        nxt = torch.where(done, torch.full_like(nxt, tokenizer.eot), nxt)
+        tokens = torch.cat([tokens, nxt[:, None]], dim=1)
+        done |= nxt == tokenizer.eot
+        if bool(done.all()):
+            break
+    out = []
+    for row in tokens[:, len(prefix):].tolist():
+        out.append(row[: row.index(tokenizer.eot)] if tokenizer.eot in row else row)
+    return out[0] if single else out
+
+
 def save_checkpoint(model: Whisper, path: str):
     torch.save({"dims": asdict(model.dims), "model_state_dict": model.state_dict()}, path)
