@@ -552,3 +552,33 @@ def test_probe_sweep_at_medium_size_every_head_bit_exact(timing, tokenizer, dev)
         st, en, _ = ref_path.boundaries_from_path(ti, tj, word_tokens)
         np.testing.assert_array_equal(res[1], st)
         np.testing.assert_array_equal(res[2], en)
+
+
+def test_medium_model_end_to_end_against_the_cpu_oracle(timing, tokenizer, oracle_models, dev):
+    """BASELINE.json's named architecture (Whisper-medium dims, seeded random init, cross-attention gain 4) on
+    TIMIT-shaped synthetic utterances: the whole B200 path (cuBLAS forward, tcgen05 attention and capture, scoring,
+    aggregation, DTW) against the CPU restatement of the reference on the same weights and inputs.  Maps within 1e-3,
+    the same top-10 heads, word boundaries equal to the frame."""
+    from oracle import ref_path
+    from whisper_char_alignment_b200 import synthetic
+
+    om = oracle_models("medium", 0, 4.0)
+    model = product_model(om, dev)
+    utts = synthetic.timit_shaped(3, tokenizer, n_mels=80, seed=4321)
+    prev_c, prev_m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ws, _ = timing.get_attentions_batch(torch.stack([u.mel for u in utts]).to(dev), [u.tokens.to(dev) for u in utts],
+                                            model, tokenizer, [u.max_frames for u in utts], 3, 1.0)
+        got = timing.force_align_batch(ws, [u.text_tokens for u in utts], tokenizer, "char", "topk", 10)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev_c, prev_m
+    for u, w, g in zip(utts, ws, got):
+        w_ref, _ = ref_path.get_attentions(u.mel, u.tokens, om, tokenizer, u.max_frames, 3, 1.0)
+        torch.testing.assert_close(w.cpu(), w_ref, rtol=1e-3, atol=1e-7)
+        want = ref_path.force_align(w_ref, u.text_tokens, tokenizer, "char", "topk", 10)
+        assert g[0] == want[0]
+        assert sorted(s[1] for s in g[4]) == sorted(s[1] for s in want[4])
+        np.testing.assert_allclose(g[3].numpy(), want[3].numpy(), rtol=1e-3, atol=1e-7)
+        np.testing.assert_array_equal(np.round(g[1] * 50).astype(int), np.round(want[1] * 50).astype(int))
+        np.testing.assert_array_equal(np.round(g[2] * 50).astype(int), np.round(want[2] * 50).astype(int))
