@@ -317,8 +317,10 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_multi_kernel(const DtwLaun
             if (warp > 0 && j <= M) {
                 // bottom row of the strip above (last lane of the previous warp), column j
                 unsigned long long w;
+                uint32_t spins = 0;
                 do {
                     w = edge_in[j - 1];
+                    if (++spins > (1u << 26)) __trap();  // a protocol bug must surface as a launch failure, not a hung GPU
                 } while ((uint32_t)(w >> 32) != (uint32_t)j);
                 up_top = __uint_as_float((uint32_t)w);
             }
