@@ -112,6 +112,13 @@ WCA_API int wca_full_attention(const float *d_q, const float *d_k, const float *
                        int n_kv, int n_heads, int head_dim, int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_out,
                        wca_stream_t stream);
 
+/* (1c) Residual add + LayerNorm of the same forward (upstream ResidualAttentionBlock: `x = x + f(ln(x))`,
+ * whisper/model.py LayerNorm = fp32 torch layer_norm): y = x + h (skipped when d_h is NULL; written when d_y is
+ * not NULL), n = (y - mean(y)) / sqrt(var(y) + eps) * gamma + beta per row, biased variance, fp32.  All
+ * matrices are row-major n_rows x width with leading dimension width; width is a multiple of 128. */
+WCA_API int wca_add_layernorm(const float *d_x, const float *d_h, const float *d_gamma, const float *d_beta, float *d_y,
+                      float *d_n, int64_t n_rows, int width, float eps, wca_stream_t stream);
+
 /* Debug only: while a non-null device buffer of >= 20000 floats is registered, CTA (0,0,0) of
  * wca_full_attention dumps its first logit block, its un-normalised output rows and the
  * softmax statistics there (tools/debug_enc_attn.py).  Pass NULL to stop. */

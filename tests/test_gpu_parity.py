@@ -582,3 +582,27 @@ def test_medium_model_end_to_end_against_the_cpu_oracle(timing, tokenizer, oracl
         np.testing.assert_allclose(g[3].numpy(), want[3].numpy(), rtol=1e-3, atol=1e-7)
         np.testing.assert_array_equal(np.round(g[1] * 50).astype(int), np.round(want[1] * 50).astype(int))
         np.testing.assert_array_equal(np.round(g[2] * 50).astype(int), np.round(want[2] * 50).astype(int))
+
+
+@pytest.mark.parametrize("width", [128, 256, 384, 512, 768, 1024, 1280])
+def test_add_layernorm_matches_torch(width, dev):
+    """wca_add_layernorm against torch's add + layer_norm in fp64 on the same inputs (rows not a multiple of the
+    8 rows a CTA handles; with and without the residual term)."""
+    from whisper_char_alignment_b200 import _cabi
+
+    g = torch.Generator(device=dev).manual_seed(width)
+    x = torch.randn(3, 37, width, device=dev, generator=g) * 3 + 0.5
+    h = torch.randn(3, 37, width, device=dev, generator=g)
+    gamma = torch.randn(width, device=dev, generator=g)
+    beta = torch.randn(width, device=dev, generator=g)
+    y, n = _cabi.add_layernorm(x, h, gamma, beta, 1e-5)
+    assert torch.equal(y, x + h)
+    want = torch.nn.functional.layer_norm((x + h).double(), (width,), gamma.double(), beta.double(), 1e-5)
+    torch.testing.assert_close(n.double(), want, rtol=1e-5, atol=1e-5)
+    y0, n0 = _cabi.add_layernorm(x, None, gamma, beta, 1e-5)
+    assert y0 is x
+    want0 = torch.nn.functional.layer_norm(x.double(), (width,), gamma.double(), beta.double(), 1e-5)
+    torch.testing.assert_close(n0.double(), want0, rtol=1e-5, atol=1e-5)
+    # no worse than torch's own fp32 kernel
+    t32 = torch.nn.functional.layer_norm(x + h, (width,), gamma, beta, 1e-5)
+    assert (n.double() - want).abs().max() <= 2 * (t32.double() - want).abs().max() + 1e-6

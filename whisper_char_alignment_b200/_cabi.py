@@ -23,7 +23,7 @@ WCA_MAX_LAYERS = 32
 ABI_VERSION = 3
 
 EXPORTS = (
-    "wca_abi_version", "wca_last_error", "wca_launch_count", "wca_device_info", "wca_capture_attention", "wca_full_attention", "wca_debug_enc_attn_buffer", "wca_debug_capture_trace", "wca_medfilt_softmax",
+    "wca_abi_version", "wca_last_error", "wca_launch_count", "wca_device_info", "wca_capture_attention", "wca_full_attention", "wca_add_layernorm", "wca_debug_enc_attn_buffer", "wca_debug_capture_trace", "wca_medfilt_softmax",
     "wca_head_scores", "wca_topk_heads", "wca_aggregate_heads", "wca_dtw_workspace_bytes", "wca_dtw_align",
 )
 
@@ -74,6 +74,7 @@ def load() -> ctypes.CDLL:
     lib.wca_capture_attention.argtypes = [vp, vp, i32, i32, i32, i64, i64, i64, i64, vp, i32, i32, i32, i32, f32, vp,
                                           ctypes.c_uint, vp]
     lib.wca_full_attention.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, vp]
+    lib.wca_add_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, f32, vp]
     lib.wca_medfilt_softmax.argtypes = [vp, i64, i64, i32, i32, f32, vp, vp]
     lib.wca_head_scores.argtypes = [vp, vp, i32, i32, i32, i32, f32, f32, f32, vp, vp]
     lib.wca_topk_heads.argtypes = [vp, vp, i32, i32, vp, vp, vp]
@@ -236,6 +237,29 @@ def full_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_heads: i
             "wca_full_attention",
         )
     return out
+
+
+def add_layernorm(x: torch.Tensor, h: torch.Tensor | None, gamma: torch.Tensor, beta: torch.Tensor, eps: float):
+    """(x + h, LayerNorm(x + h) * gamma + beta) over the last dimension in one pass (wca_add_layernorm);
+    h may be None (plain LayerNorm, returns (x, n))."""
+    width = x.shape[-1]
+    for t, name in ((x, "x"), (h, "h"), (gamma, "gamma"), (beta, "beta")):
+        if t is None:
+            continue
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise WcaError(f"add_layernorm: {name} must be a contiguous fp32 CUDA tensor (no CPU fallback exists)")
+    if h is not None and h.shape != x.shape:
+        raise WcaError("add_layernorm: x and h must have the same shape")
+    y = torch.empty_like(x) if h is not None else x
+    n = torch.empty_like(x)
+    with _timed("wca_add_layernorm"):
+        _check(
+            load().wca_add_layernorm(x.data_ptr(), None if h is None else h.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                     None if h is None else y.data_ptr(), n.data_ptr(), x.numel() // width, width,
+                                     float(eps), _stream()),
+            "wca_add_layernorm",
+        )
+    return y, n
 
 
 def encoder_attention(q, k, v, n_heads, out=None):

@@ -57,6 +57,8 @@ int launch_full_attention(const float *, const float *, const float *, float *, 
                           int64_t, cudaStream_t);
 
 void set_enc_attn_debug_buffer(float *);
+int launch_add_layernorm(const float *, const float *, const float *, const float *, float *, float *, int64_t, int, float,
+                         cudaStream_t);
 
 static bool odd_width_ok(int w) { return w >= 1 && w <= WCA_MAX_MEDFILT && (w & 1) == 1; }
 
@@ -152,6 +154,17 @@ int wca_full_attention(const float *d_q, const float *d_k, const float *d_v, flo
     }
     return launch_full_attention(d_q, d_k, d_v, d_out, n_batch, n_q, n_kv, n_heads, ld_q, ld_k, ld_v, ld_out,
                                  static_cast<cudaStream_t>(stream));
+}
+
+int wca_add_layernorm(const float *d_x, const float *d_h, const float *d_gamma, const float *d_beta, float *d_y, float *d_n,
+                      int64_t n_rows, int width, float eps, wca_stream_t stream) {
+    WCA_CHECK_ARG(d_x && d_gamma && d_beta && d_n, "wca_add_layernorm: null pointer");
+    WCA_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31) * 8, "wca_add_layernorm: n_rows=%lld", (long long)n_rows);
+    WCA_CHECK_ARG(width > 0 && width % 128 == 0, "wca_add_layernorm: width=%d must be a multiple of 128", width);
+    WCA_CHECK_ARG(((uintptr_t)d_x | (uintptr_t)d_h | (uintptr_t)d_gamma | (uintptr_t)d_beta | (uintptr_t)d_y | (uintptr_t)d_n) % 16 == 0,
+                  "wca_add_layernorm: pointers must be 16-byte aligned");
+    if (n_rows == 0) return WCA_OK;
+    return launch_add_layernorm(d_x, d_h, d_gamma, d_beta, d_y, d_n, n_rows, width, eps, static_cast<cudaStream_t>(stream));
 }
 
 void wca_debug_enc_attn_buffer(float *d_buf) { set_enc_attn_debug_buffer(d_buf); }

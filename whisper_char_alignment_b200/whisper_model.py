@@ -108,6 +108,24 @@ class Attention(nn.Module):
         return self.out(ctx.transpose(1, 2).flatten(2)), None
 
 
+#: "wca": residual add + LayerNorm pairs run as one sm_100a kernel (csrc/layernorm.cu); "torch": separate ops.
+ADD_LAYERNORM = os.environ.get("WCA_ADD_LAYERNORM", "wca")
+
+
+def _add_ln(x, h, ln):
+    """(x + h, ln(x + h)); h None -> (x, ln(x)).  One fused kernel for fp32 CUDA tensors of a supported width."""
+    if (ADD_LAYERNORM == "wca" and x.is_cuda and x.dtype == torch.float32 and x.shape[-1] % 128 == 0
+            and x.shape[-1] // 128 in (1, 2, 3, 4, 6, 8, 10) and ln.weight.dtype == torch.float32):
+        from . import _cabi
+
+        x = x if x.is_contiguous() else x.contiguous()
+        if h is not None and not h.is_contiguous():
+            h = h.contiguous()
+        return _cabi.add_layernorm(x, h, ln.weight, ln.bias, ln.eps)
+    y = x if h is None else x + h
+    return y, ln(y)
+
+
 class Block(nn.Module):
     def __init__(self, width: int, heads: int, cross: bool):
         super().__init__()
@@ -118,11 +136,17 @@ class Block(nn.Module):
         self.mlp = nn.Sequential(_Proj(width, 4 * width), nn.GELU(), _Proj(4 * width, width))
         self.mlp_ln = _Norm(width)
 
-    def forward(self, x, xa=None, causal: bool = False):
-        x = x + self.attn(self.attn_ln(x), causal=causal)[0]
+    def forward(self, x, xa=None, causal: bool = False, pending=None):
+        """Upstream: x += attn(ln(x)); x += cross_attn(ln(x), xa); x += mlp(ln(x)).  Every residual add is
+        paired with the LayerNorm that follows it, so the last add of a block is handed to the next one
+        (`pending`): returns (x, h) with the block's output being x + h."""
+        x, n = _add_ln(x, pending, self.attn_ln)
+        h = self.attn(n, causal=causal)[0]
         if self.cross_attn is not None:
-            x = x + self.cross_attn(self.cross_attn_ln(x), xa)[0]
-        return x + self.mlp(self.mlp_ln(x))
+            x, n = _add_ln(x, h, self.cross_attn_ln)
+            h = self.cross_attn(n, xa)[0]
+        x, n = _add_ln(x, h, self.mlp_ln)
+        return x, self.mlp(n)
 
 
 def _sinusoid_table(length: int, width: int, max_timescale: float = 10000.0):
@@ -161,9 +185,10 @@ class AudioEncoder(nn.Module):
         if x.shape[1:] != self.positional_embedding.shape:
             raise ValueError(f"incorrect audio shape {tuple(mel.shape)}: expected {2 * self.positional_embedding.shape[0]} frames")
         x = (x + self.positional_embedding).to(x.dtype)
+        pending = None
         for blk in self.blocks:
-            x = blk(x)
-        return self.ln_post(x)
+            x, pending = blk(x, pending=pending)
+        return _add_ln(x, pending, self.ln_post)[1]
 
 
 class TextDecoder(nn.Module):
@@ -177,9 +202,10 @@ class TextDecoder(nn.Module):
     def forward(self, tokens, xa):
         x = self.token_embedding(tokens) + self.positional_embedding[: tokens.shape[-1]]
         x = x.to(xa.dtype)
+        pending = None
         for blk in self.blocks:
-            x = blk(x, xa, causal=True)
-        x = self.ln(x)
+            x, pending = blk(x, xa, causal=True, pending=pending)
+        x = _add_ln(x, pending, self.ln)[1]
         return (x @ self.token_embedding.weight.to(x.dtype).t()).float()
 
 
