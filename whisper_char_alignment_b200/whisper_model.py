@@ -165,23 +165,24 @@ class AudioEncoder(nn.Module):
         self.blocks = nn.ModuleList([Block(width, heads, cross=False) for _ in range(layers)])
         self.ln_post = _Norm(width)
 
-    def _conv2_as_gemm(self, x):
-        """conv2 (kernel 3, stride 2, padding 1) as ONE cuBLAS GEMM over unfolded windows: same sums in
-        another order, output already in the (batch, frames, width) layout the blocks want.  cuDNN's
-        fp32 path for this shape is a CUDA-core kernel (3% of a step) and hands back (batch, width,
+    @staticmethod
+    def _conv_as_gemm(x, conv):
+        """Conv1d (kernel 3, padding 1, stride 1 or 2) over a (batch, frames, channels) tensor as ONE cuBLAS GEMM on
+        unfolded windows: the same sums in another order, output again (batch, frames, channels) -- the layout the
+        blocks want.  cuDNN's fp32 path for these shapes is a CUDA-core kernel and hands back (batch, channels,
         frames), which made every LayerNorm of the encoder copy a permuted residual stream."""
-        b, c, _ = x.shape
-        cols = F.pad(x, (1, 1)).unfold(2, 3, 2)                      # (b, c, frames_out, 3) view
-        cols = cols.permute(0, 2, 1, 3).reshape(b * cols.shape[2], c * 3)
-        w = self.conv2.weight.to(x.dtype).reshape(self.conv2.out_channels, c * 3)
-        return torch.addmm(self.conv2.bias.to(x.dtype), cols, w.t()).view(b, -1, self.conv2.out_channels)
+        b, _, c = x.shape
+        cols = F.pad(x, (0, 0, 1, 1)).unfold(1, 3, conv.stride[0])       # (b, frames_out, c, 3) view
+        cols = cols.reshape(b * cols.shape[1], c * 3)
+        w = conv.weight.to(x.dtype).reshape(conv.out_channels, c * 3)
+        return torch.addmm(conv.bias.to(x.dtype), cols, w.t()).view(b, -1, conv.out_channels)
 
     def forward(self, mel):
-        x = F.gelu(self.conv1(mel))
-        if x.is_cuda and x.dtype == torch.float32:
-            x = F.gelu(self._conv2_as_gemm(x))
+        if mel.is_cuda and mel.dtype == torch.float32:
+            x = F.gelu(self._conv_as_gemm(mel.transpose(1, 2).contiguous(), self.conv1))
+            x = F.gelu(self._conv_as_gemm(x, self.conv2))
         else:
-            x = F.gelu(self.conv2(x)).transpose(1, 2).contiguous()
+            x = F.gelu(self.conv2(F.gelu(self.conv1(mel)))).transpose(1, 2).contiguous()
         if x.shape[1:] != self.positional_embedding.shape:
             raise ValueError(f"incorrect audio shape {tuple(mel.shape)}: expected {2 * self.positional_embedding.shape[0]} frames")
         x = (x + self.positional_embedding).to(x.dtype)
@@ -206,7 +207,22 @@ class TextDecoder(nn.Module):
         for blk in self.blocks:
             x, pending = blk(x, xa, causal=True, pending=pending)
         x = _add_ln(x, pending, self.ln)[1]
-        return (x @ self.token_embedding.weight.to(x.dtype).t()).float()
+        return self._vocab_logits(x)
+
+    def _vocab_logits(self, x):
+        """x @ E^T.  n_vocab (51865 / 51866) is odd or not a multiple of 4, so the output rows are misaligned and
+        cuBLAS falls back to a CUDA-core SGEMM; on the device the product is computed against a copy of E padded
+        to a multiple of 16 rows (cached, rebuilt when the weight changes) and the padding columns are dropped."""
+        w = self.token_embedding.weight
+        if not (x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32) or w.shape[0] % 16 == 0:
+            return (x @ w.to(x.dtype).t()).float()
+        key = (w.data_ptr(), w._version, w.device)
+        if getattr(self, "_padded_key", None) != key:
+            rows = (w.shape[0] + 15) // 16 * 16
+            padded = torch.zeros(rows, w.shape[1], dtype=w.dtype, device=w.device)
+            padded[: w.shape[0]] = w.detach()
+            self._padded_vocab, self._padded_key = padded, key
+        return F.linear(x, self._padded_vocab)[..., : w.shape[0]]
 
 
 class Whisper(nn.Module):
