@@ -11,13 +11,18 @@
 // for BOTH contractions (Q K^T and P V), 3 x tcgen05.mma.kind::tf32 each.
 //
 // One CTA = 128 queries of one (batch, head); keys are swept in blocks of 64.
-//   TMEM (512 columns)  Q_hi | Q_lo | S0 | S1 | P_lo0 | P_lo1 | T0 | T1    (64 columns each)
+//   TMEM (512 columns)  Q_hi | Q_lo | S0 | S1 | S2 | P_lo0 | P_lo1 | T      (64 columns each)
+//                       Three S buffers: the dependency cycle of one buffer (Q K^T -> softmax -> P V ->
+//                       next Q K^T into it) is ~3 700 cycles, so with two buffers a key block could not
+//                       take less than ~1 850 cycles although its MMAs need 1 536; P_lo needs only two
+//                       buffers and T one (it is folded into registers before the next P V lands).
 //                       Q and P are A operands read straight from tensor memory (tcgen05.mma
 //                       with [a_tmem]); P_hi overwrites S in place.  T_b = P_j V_j of ONE key block
 //                       (24 MMAs); the blocks are summed in fp32 registers with round-to-nearest,
 //                       because the tensor core truncates when it accumulates: a 576-MMA chain into
 //                       one accumulator drifts by ~1e-5 relative, a 24-MMA chain by ~1e-6.
-//   shared memory       3-stage ring of {K_hi, V_hi, K_lo, V_lo} (16 KB each).  TMA lands K and V
+//   shared memory       3-stage ring of {K_hi, V_hi, K_lo, V_lo} (16 KB each), K and V halves released and
+//                       refilled independently (K right after Q K^T, V after P V).  TMA lands K and V
 //                       with the 128-byte swizzle; that IS the UMMA canonical layout (K-major for
 //                       K in Q K^T, MN-major for V in P V), so the split is a linear sweep that
 //                       leaves the tile alone (it is hi) and writes lo to a twin tile.
@@ -59,24 +64,31 @@ constexpr int kOffQ = 0;
 constexpr int kOffStage = kOffQ + kQBytes;
 constexpr int kOffFactor = kOffStage + kStages * kStageBytes;   // [4][128] rescale factors + [128] row sums
 constexpr int kOffBar = kOffFactor + 5 * kQRows * 4;
+constexpr int kSBufs = 3;  // S / P_hi buffers in tensor memory
 enum Bar {
     kQFull = 0,
     kQReady = 1,
-    kKvFull = 2,
-    kKvSplit = kKvFull + kStages,
-    kKvEmpty = kKvSplit + kStages,
-    kSFull = kKvEmpty + kStages,
-    kPReady = kSFull + 2,
-    kPvDone = kPReady + 2,   // count 1 (tcgen05.commit); waited by the softmax AND the accumulate warpgroup
-    kTFree = kPvDone + 2,    // accumulate warpgroup has read T[b]
-    kLReady = kTFree + 2,    // row sums published
+    // K and V of a stage have their own barrier rings: the K half is free as soon as Q K_j^T has run, a whole
+    // softmax + P V earlier than the V half, so K_{j+3} is fetched and split while block j is still in flight
+    kKFull = 2,
+    kVFull = kKFull + kStages,
+    kKSplit = kVFull + kStages,
+    kVSplit = kKSplit + kStages,
+    kKEmpty = kVSplit + kStages,
+    kVEmpty = kKEmpty + kStages,
+    kSFull = kVEmpty + kStages,   // the per-key-block barriers below form rings of kSBufs
+    kPHi = kSFull + kSBufs,        // softmax -> accumulate warpgroup: P (= P_hi) stored in S[b]
+    kPReady = kPHi + kSBufs,       // accumulate warpgroup -> P V issuer: P_lo stored as well
+    kPvDone = kPReady + kSBufs,    // count 1 (tcgen05.commit); waited by the Q K^T issuer, the softmax AND the accumulate warpgroup
+    kTFree = kPvDone + kSBufs,     // accumulate warpgroup has read T
+    kLReady = kTFree + 1,          // row sums published
     kNumBars = kLReady + 1
 };
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
-constexpr uint32_t kColQHi = 0, kColQLo = 64, kColS = 128, kColPLo = 256, kColT = 384, kTmemCols = 512;
+constexpr uint32_t kColQHi = 0, kColQLo = 64, kColS = 128, kColPLo = 320, kColT = 448, kTmemCols = 512;
 constexpr float kRescaleGap = 32.f;  // log2 units
 
 __device__ __forceinline__ void tma_load_box3(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
@@ -115,23 +127,33 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
     const uint32_t bars = smem_u32(smem + kOffBar);
     auto bar = [&](int which) { return bars + 8u * (uint32_t)which; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kOffTmem);
+    // One arrival per warp: every lane has finished (and fenced) its part, the warp converges, lane 0 arrives
+    // (128 threads arriving on one mbarrier word serialise on it).
+    auto warp_arrive = [&](uint32_t b) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b);
+    };
     const bool tr = a.dbg != nullptr && blockIdx.x + blockIdx.y + blockIdx.z == 0 && lane == 0 && (warp < 2 || (warp & 3) == 2);  // incl. warp 14
 
     if (tid == 0) {
         mbar_init(bar(kQFull), 1);
-        mbar_init(bar(kQReady), 128);
+        mbar_init(bar(kQReady), 4);
         for (int i = 0; i < kStages; ++i) {
-            mbar_init(bar(kKvFull + i), 1);
-            mbar_init(bar(kKvSplit + i), 128);
-            mbar_init(bar(kKvEmpty + i), 1);
+            mbar_init(bar(kKFull + i), 1);
+            mbar_init(bar(kVFull + i), 1);
+            mbar_init(bar(kKSplit + i), 4);
+            mbar_init(bar(kVSplit + i), 4);
+            mbar_init(bar(kKEmpty + i), 1);
+            mbar_init(bar(kVEmpty + i), 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kSBufs; ++i) {
             mbar_init(bar(kSFull + i), 1);
-            mbar_init(bar(kPReady + i), 128);
+            mbar_init(bar(kPHi + i), 4);
+            mbar_init(bar(kPReady + i), 4);
             mbar_init(bar(kPvDone + i), 1);
-            mbar_init(bar(kTFree + i), 128);
         }
-        mbar_init(bar(kLReady), 128);
+        mbar_init(bar(kTFree), 4);
+        mbar_init(bar(kLReady), 4);
         fence_mbar_init();
     }
     if (warp == 0) {
@@ -152,16 +174,25 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
             mbar_expect_tx(bar(kQFull), kQBytes);
             tma_load_box3(smem_u32(smem + kOffQ), &maps.q, col0, q0, batch, bar(kQFull));
             tma_load_box3(smem_u32(smem + kOffQ) + kQBoxBytes, &maps.q, col0 + kBoxCols, q0, batch, bar(kQFull));
-            for (int j = 0; j < n_blocks; ++j) {
-                const int s = j % kStages;
-                mbar_wait(bar(kKvEmpty + s), ((j / kStages) & 1) ^ 1);  // first lap passes immediately
-                stamp(a.dbg, tr, kEvTmaIssue, j);
-                const uint32_t dst = smem_u32(smem + kOffStage + s * kStageBytes);
-                mbar_expect_tx(bar(kKvFull + s), kRawBytes);  // rows past n_ctx are zero-filled, boxes are always full
-                tma_load_box3(dst, &maps.k, col0, j * kKeys, batch, bar(kKvFull + s));
-                tma_load_box3(dst + kKvBoxBytes, &maps.k, col0 + kBoxCols, j * kKeys, batch, bar(kKvFull + s));
-                tma_load_box3(dst + kOpBytes, &maps.v, col0, j * kKeys, batch, bar(kKvFull + s));
-                tma_load_box3(dst + kOpBytes + kKvBoxBytes, &maps.v, col0 + kBoxCols, j * kKeys, batch, bar(kKvFull + s));
+            // issue order K_0, K_1, V_0, K_2, V_1, ...: K runs one block ahead of V
+            for (int t = 0; t <= n_blocks; ++t) {
+                if (t < n_blocks) {
+                    const int s = t % kStages;
+                    mbar_wait(bar(kKEmpty + s), ((t / kStages) & 1) ^ 1);  // first lap passes immediately
+                    stamp(a.dbg, tr, kEvTmaIssue, t);
+                    const uint32_t dst = smem_u32(smem + kOffStage + s * kStageBytes);
+                    mbar_expect_tx(bar(kKFull + s), kOpBytes);  // rows past n_ctx are zero-filled, boxes are always full
+                    tma_load_box3(dst, &maps.k, col0, t * kKeys, batch, bar(kKFull + s));
+                    tma_load_box3(dst + kKvBoxBytes, &maps.k, col0 + kBoxCols, t * kKeys, batch, bar(kKFull + s));
+                }
+                if (t >= 1) {
+                    const int i = t - 1, s = i % kStages;
+                    mbar_wait(bar(kVEmpty + s), ((i / kStages) & 1) ^ 1);
+                    const uint32_t dst = smem_u32(smem + kOffStage + s * kStageBytes) + kOpBytes;
+                    mbar_expect_tx(bar(kVFull + s), kOpBytes);
+                    tma_load_box3(dst, &maps.v, col0, i * kKeys, batch, bar(kVFull + s));
+                    tma_load_box3(dst + kKvBoxBytes, &maps.v, col0 + kBoxCols, i * kKeys, batch, bar(kVFull + s));
+                }
             }
         }
         __syncwarp();
@@ -175,9 +206,9 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
         mbar_wait(bar(kQReady), 0);
         for (int j = 0; j < n_blocks; ++j) {
             // ---- S[j & 1] = Q K_j^T
-            const int s = j % kStages, b = j & 1;
-            mbar_wait(bar(kKvSplit + s), (j / kStages) & 1);
-            if (j >= 2) mbar_wait(bar(kPvDone + b), ((j - 2) >> 1) & 1);  // P V of block j-2 no longer reads P_hi = S[b]
+            const int s = j % kStages, b = j % kSBufs;
+            mbar_wait(bar(kKSplit + s), (j / kStages) & 1);
+            if (j >= kSBufs) mbar_wait(bar(kPvDone + b), ((j - kSBufs) / kSBufs) & 1);  // P V of block j-3 no longer reads P_hi = S[b]
             tc_fence_after();
             stamp(a.dbg, tr, kEvQkIssue, j);
             const uint32_t k_hi = stage0 + (uint32_t)s * kStageBytes;
@@ -197,6 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
                                      (pass | ks) != 0, elected);
                 }
             }
+            umma_commit_if(bar(kKEmpty + s), elected);
             umma_commit_if(bar(kSFull + b), elected);
             stamp(a.dbg, tr, kEvQkIssued, j);
         }
@@ -209,13 +241,14 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
         const uint32_t skip_pv = a.skip & 2;
         for (int i = 0; i < n_blocks; ++i) {
             // ---- T[i & 1] = P_i V_i
-            const int s = i % kStages, b = i & 1;
-            mbar_wait(bar(kPReady + b), (i >> 1) & 1);
-            if (i >= 2) mbar_wait(bar(kTFree + b), ((i - 2) >> 1) & 1);  // T[b] of block i-2 has been folded
+            const int s = i % kStages, b = i % kSBufs;
+            mbar_wait(bar(kVSplit + s), (i / kStages) & 1);
+            mbar_wait(bar(kPReady + b), (i / kSBufs) & 1);
+            if (i >= 1) mbar_wait(bar(kTFree), (i - 1) & 1);  // T of block i-1 has been folded into the O registers
             tc_fence_after();
             stamp(a.dbg, tr, kEvPReady, i);
             const uint32_t v_hi = stage0 + (uint32_t)s * kStageBytes + kOpBytes;
-            const uint32_t p_hi = tm + kColS + (uint32_t)b * kKeys, p_lo = tm + kColPLo + (uint32_t)b * kKeys;
+            const uint32_t p_hi = tm + kColS + (uint32_t)b * kKeys, p_lo = tm + kColPLo + (uint32_t)(i & 1) * kKeys;
             // MN-major, 128B swizzle with 32B atoms: 4 keys x 128 B per atom, so the 8 keys of one MMA are
             // two atoms SBO = 512 B apart; the two 32-float halves of d are LBO apart
             const uint64_t dv_hi = smem_desc_sw128(v_hi, kKvBoxBytes, 512, kSw128Base32);
@@ -227,11 +260,11 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
                     const uint64_t db = pass == 1 ? dv_lo : dv_hi;
 #pragma unroll
                     for (int ks = 0; ks < kKeys / 8; ++ks)
-                        umma_tf32_ts(tm + kColT + (uint32_t)b * kHeadDim, a_col + (uint32_t)(ks * 8),
+                        umma_tf32_ts(tm + kColT, a_col + (uint32_t)(ks * 8),
                                      db + (uint64_t)((ks * 1024) >> 4), idesc_pv, (pass | ks) != 0, elected);
                 }
             }
-            umma_commit_if(bar(kKvEmpty + s), elected);
+            umma_commit_if(bar(kVEmpty + s), elected);
             umma_commit_if(bar(kPvDone + b), elected);
             stamp(a.dbg, tr, kEvPvIssued, i);
         }
@@ -263,24 +296,36 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
             }
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(bar(kQReady));
+            warp_arrive(bar(kQReady));
         }
-        for (int j = 0; j < n_blocks; ++j) {
-            const int s = j % kStages;
-            mbar_wait(bar(kKvFull + s), (j / kStages) & 1);
-            stamp(a.dbg, tr, kEvKvFull, j);
-            const float4 *raw = reinterpret_cast<const float4 *>(smem + kOffStage + s * kStageBytes);
-            float4 *twin = reinterpret_cast<float4 *>(smem + kOffStage + s * kStageBytes + kRawBytes);
-            constexpr int kIters = kRawBytes / 16 / 128;  // 16 float4 per thread
-#pragma unroll 4
-            for (int it = (a.skip & 8) ? kIters : 0; it < kIters; ++it) {
-                const int idx = it * 128 + t;
-                const float4 v = raw[idx];
-                twin[idx] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));  // hi = the raw tile
-            }
+        // lo twin of one operand (K or V) of a stage: linear sweep, hi = the raw tile
+        auto split_op = [&](int stage, int op) {
+            const float4 *raw = reinterpret_cast<const float4 *>(smem + kOffStage + stage * kStageBytes + op * kOpBytes);
+            float4 *twin = reinterpret_cast<float4 *>(smem + kOffStage + stage * kStageBytes + kRawBytes + op * kOpBytes);
+            constexpr int kIters = kOpBytes / 16 / 128;  // 8 float4 per thread
+            float4 v[kIters];
+#pragma unroll
+            for (int it = 0; it < kIters; ++it) v[it] = raw[it * 128 + t];
+#pragma unroll
+            for (int it = 0; it < kIters; ++it)
+                twin[it * 128 + t] = make_float4(tf32_lo(v[it].x), tf32_lo(v[it].y), tf32_lo(v[it].z), tf32_lo(v[it].w));
             fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
-            mbar_arrive(bar(kKvSplit + s));
-            stamp(a.dbg, tr, kEvSplitDone, j);
+        };
+        for (int tt = 0; tt <= n_blocks; ++tt) {  // same order as the producer: K_0, K_1, V_0, K_2, V_1, ...
+            if (tt < n_blocks) {
+                const int s = tt % kStages;
+                mbar_wait(bar(kKFull + s), (tt / kStages) & 1);
+                stamp(a.dbg, tr, kEvKvFull, tt);
+                if (!(a.skip & 8)) split_op(s, 0);
+                warp_arrive(bar(kKSplit + s));
+                stamp(a.dbg, tr, kEvSplitDone, tt);
+            }
+            if (tt >= 1) {
+                const int i = tt - 1, s = i % kStages;
+                mbar_wait(bar(kVFull + s), (i / kStages) & 1);
+                if (!(a.skip & 8)) split_op(s, 1);
+                warp_arrive(bar(kVSplit + s));
+            }
         }
     } else if (warp >= 6 && warp < 10) {
         // ================= softmax: thread <-> query row =================
@@ -290,9 +335,9 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
         float *factor = reinterpret_cast<float *>(smem + kOffFactor);  // [4][128] rescale factors, ring over blocks
         float m_ref = 0.f, l_sum = 0.f;
         for (int j = 0; j < n_blocks; ++j) {
-            const int b = j & 1;
+            const int b = j % kSBufs;
             const int n_valid = min(kKeys, a.n_ctx - j * kKeys);  // < 64 only for the last block
-            mbar_wait(bar(kSFull + b), (j >> 1) & 1);
+            mbar_wait(bar(kSFull + b), (j / kSBufs) & 1);
             tc_fence_after();
             stamp(a.dbg, tr, kEvSFull, j);
             const uint32_t s_col = trow + kColS + (uint32_t)b * kKeys;
@@ -369,25 +414,17 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
             l_sum += (lpart[0] + lpart[1]) + (lpart[2] + lpart[3]);
             stamp(a.dbg, tr, kEvExpDone, j);
             factor[(j & 3) * kQRows + row] = f;  // read by the accumulate thread of this row after P V of block j
-            if (j >= 2) {  // P V of block j-2 has finished reading P_hi (= S[b]) and P_lo[b]
-                mbar_wait(bar(kPvDone + b), ((j - 2) >> 1) & 1);
-                tc_fence_after();
-            }
+            // P is stored as it is (the tensor core chops it to P_hi); the accumulate warpgroup derives P_lo from it,
+            // so this warpgroup -- the one every key block has to pass through -- is done a store round trip earlier
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float lo[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) lo[e] = tf32_lo(sv[q][e]);
-                tmem_st16(s_col + (uint32_t)(q * 16), sv[q]);  // P_hi = p as is (the tensor core chops it)
-                tmem_st16(trow + kColPLo + (uint32_t)(b * kKeys + q * 16), lo);
-            }
+            for (int q = 0; q < 4; ++q) tmem_st16(s_col + (uint32_t)(q * 16), sv[q]);
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(bar(kPReady + b));
+            warp_arrive(bar(kPHi + b));
             stamp(a.dbg, tr, kEvPArrive, j);
         }
         factor[4 * kQRows + row] = l_sum;
-        mbar_arrive(bar(kLReady));
+        warp_arrive(bar(kLReady));
     } else if (warp >= 10) {
         // ================= accumulate + epilogue: thread <-> query row =================
         // acc = this row of O, summed over key blocks in fp32 registers with round-to-nearest.
@@ -399,16 +436,16 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
         for (int q = 0; q < 4; ++q)
 #pragma unroll
             for (int e = 0; e < 16; ++e) acc[q][e] = 0.f;
-        for (int j = 0; j < n_blocks; ++j) {
-            const int b = j & 1;
-            mbar_wait(bar(kPvDone + b), (j >> 1) & 1);
+        // acc += T once P_i V_i has landed (T is single: P V of block i+1 waits for this)
+        auto fold = [&](int i) {
+            mbar_wait(bar(kPvDone + i % kSBufs), (i / kSBufs) & 1);
             tc_fence_after();
-            stamp(a.dbg, tr, kEvPvDone, j);
+            stamp(a.dbg, tr, kEvPvDone, i);
             float t[2][16];  // two chunks in flight
-            const uint32_t t_col = trow + kColT + (uint32_t)(b * kHeadDim);
+            const uint32_t t_col = trow + kColT;
             tmem_ld16_issue(t_col, t[0]);
-            const float f = *reinterpret_cast<const volatile float *>(&factor[(j & 3) * kQRows + row]);
-            if (f != 1.f) {  // the reference moved at block j: everything before it is rescaled
+            const float f = *reinterpret_cast<const volatile float *>(&factor[(i & 3) * kQRows + row]);
+            if (f != 1.f) {  // the reference moved at block i: everything before it is rescaled
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -422,9 +459,34 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
                 for (int e = 0; e < 16; ++e) acc[q][e] += t[q & 1][e];
             }
             tc_fence_before();
-            mbar_arrive(bar(kTFree + b));
-            stamp(a.dbg, tr, kEvFoldDone, j);
+            warp_arrive(bar(kTFree));
+            stamp(a.dbg, tr, kEvFoldDone, i);
+        };
+        for (int j = 0; j < n_blocks; ++j) {
+            // P_lo of block j from the P the softmax warpgroup left in S[b]; P_lo[j & 1] is free: the fold of block
+            // j-2 (previous iteration) waited for its P V.  Done BEFORE folding block j-1 so that it overlaps P V_{j-1}.
+            const int b = j % kSBufs;
+            mbar_wait(bar(kPHi + b), (j / kSBufs) & 1);
+            tc_fence_after();
+            const uint32_t p_col = trow + kColS + (uint32_t)b * kKeys;
+            const uint32_t lo_col = trow + kColPLo + (uint32_t)(j & 1) * kKeys;
+            float pv[2][16];
+            tmem_ld16_issue(p_col, pv[0]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q + 1 < 4) tmem_ld16_issue(p_col + (uint32_t)((q + 1) * 16), pv[(q + 1) & 1]);
+                tmem_ld_wait(pv[q & 1]);
+                float lo[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) lo[e] = tf32_lo(pv[q & 1][e]);
+                tmem_st16(lo_col + (uint32_t)(q * 16), lo);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            warp_arrive(bar(kPReady + b));
+            if (j >= 1) fold(j - 1);
         }
+        fold(n_blocks - 1);
         // ---- epilogue: O / l -> global
         mbar_wait(bar(kLReady), 0);
         const float l_sum = *reinterpret_cast<const volatile float *>(&factor[4 * kQRows + row]);
