@@ -355,8 +355,18 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
             // Streaming pass against the CURRENT reference: p = 2^(s c - m_ref) and the block maximum are
             // computed together, chunk by chunk as the tensor-memory loads land (four independent chains).
             float bmax[4], lpart[4];
+            if (j == 0) {
+                // no reference yet: take the maximum of the first 16 keys.  Anything within 2^32 of the row maximum
+                // will do (the lazy rescale below catches the rest), and it keeps block 0 on the hot path.
+                tmem_ld_wait(sv[0]);
+                float mx = sv[0][0];
+#pragma unroll
+                for (int e = 1; e < 16; ++e) mx = (n_valid == kKeys || e < n_valid) ? fmaxf(mx, sv[0][e]) : mx;
+                m_ref = mx * c;
+            }
             const float neg_m = -m_ref;
-            if (n_valid == kKeys) {
+            const bool full = n_valid == kKeys;  // only the last block of a context that is not a multiple of 64 is ragged
+            if (full) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     tmem_ld_wait(sv[q]);
@@ -370,29 +380,24 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
                     bmax[q] = mx;
                     lpart[q] = ls;
                 }
-            } else {  // last block of a context that is not a multiple of 64: keys >= n_valid do not exist
+            } else {  // ragged block: only its maximum here, the masked exponentials come from the generic path below
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     tmem_ld_wait(sv[q]);
-                    float mx = -INFINITY, ls = 0.f;
+                    float mx = -INFINITY;
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const bool ok = q * 16 + e < n_valid;
-                        mx = ok ? fmaxf(mx, sv[q][e]) : mx;
-                        sv[q][e] = ok ? ex2_approx(fmaf(sv[q][e], c, neg_m)) : 0.f;
-                        ls += sv[q][e];
-                    }
+                    for (int e = 0; e < 16; ++e) mx = (q * 16 + e < n_valid) ? fmaxf(mx, sv[q][e]) : mx;
                     bmax[q] = mx;
-                    lpart[q] = ls;
+                    lpart[q] = 0.f;
                 }
             }
             const float bm = fmaxf(fmaxf(bmax[0], bmax[1]), fmaxf(bmax[2], bmax[3])) * c;
             float f = 1.f;
-            // Block 0 has no reference yet; later blocks move it only when they exceed it by 2^32 (rare).
-            const bool need = j == 0 || bm > m_ref + kRescaleGap;
-            if (__any_sync(0xffffffffu, need)) {
+            // The reference moves only when a block exceeds it by 2^32 (rare); the same generic path serves ragged blocks.
+            const bool need = bm > m_ref + kRescaleGap;
+            if (__any_sync(0xffffffffu, need) || !full) {
                 if (need) {
-                    f = j == 0 ? 1.f : ex2_approx(m_ref - bm);
+                    f = j == 0 ? 1.f : ex2_approx(m_ref - bm);  // nothing accumulated yet in block 0
                     m_ref = bm;
                     l_sum *= f;
                 }
@@ -491,20 +496,34 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
         mbar_wait(bar(kLReady), 0);
         const float l_sum = *reinterpret_cast<const volatile float *>(&factor[4 * kQRows + row]);
         const float inv = 1.f / l_sum;
-        const bool row_ok = q0 + row < a.n_q;
-        float *dst = a.out + ((int64_t)batch * a.n_q + q0 + row) * a.ld_out + col0;
+        if (a.dbg && blockIdx.x + blockIdx.y + blockIdx.z == 0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (a.dbg && blockIdx.x + blockIdx.y + blockIdx.z == 0) {
+            for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int e = 0; e < 16; ++e) a.dbg[8192 + row * 64 + q * 16 + e] = acc[q][e];
-                a.dbg[16384 + row] = l_sum;
-            }
-            if (row_ok) {
+            a.dbg[16384 + row] = l_sum;
+        }
+        // A thread owns a row, but 32 lanes storing 16 bytes of 32 different rows is 32 memory requests per
+        // instruction.  The rows go through the Q staging tile (free since Q was split into tensor memory): each warp
+        // writes its 32 rows with the 16-byte chunks XOR-swizzled by the row, then stores two full 256-byte rows per
+        // instruction.
+        float4 *stage = reinterpret_cast<float4 *>(smem + kOffQ) + (warp & 3) * 32 * 16;  // [32 rows][16 chunks]
 #pragma unroll
-                for (int e = 0; e < 16; e += 4)
-                    *reinterpret_cast<float4 *>(dst + q * 16 + e) =
-                        make_float4(acc[q][e] * inv, acc[q][e + 1] * inv, acc[q][e + 2] * inv, acc[q][e + 3] * inv);
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+                stage[lane * 16 + ((q * 4 + e / 4) ^ (lane & 15))] =
+                    make_float4(acc[q][e] * inv, acc[q][e + 1] * inv, acc[q][e + 2] * inv, acc[q][e + 3] * inv);
+        __syncwarp();
+        {
+            const int ch = lane & 15, sub = lane >> 4;
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int r = 2 * i + sub;                 // row within this warp's 32
+                const int grow = q0 + (warp & 3) * 32 + r;  // query row
+                const float4 v = stage[r * 16 + (ch ^ (r & 15))];
+                if (grow < a.n_q)
+                    *reinterpret_cast<float4 *>(a.out + ((int64_t)batch * a.n_q + grow) * a.ld_out + col0 + ch * 4) = v;
             }
         }
     }
