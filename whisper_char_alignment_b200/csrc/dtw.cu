@@ -22,6 +22,8 @@
 // strictly smaller than both others, otherwise the time step -- so ties and NaN go to
 // code 2 (even when that is not the minimum).  Border rule of backtrace: column 0 -> code 1,
 // row 0 -> code 2.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace wca {
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
 // arrives by __shfl_up as before; between warps lane 31 of warp w publishes the bottom row of its strip,
 // column by column, in a shared line `edge[w][j]` followed by a progress counter, and lane 0 of warp w + 1
 // (which runs 32 steps behind by construction) polls the counter: no block barrier on the recurrence.
-template <int R, int WPP>
+template <int R, int WPP, int kAhead>
 __global__ void __launch_bounds__(32 * WPP) dtw_align_multi_kernel(const DtwLaunch p) {
     using Word = typename TraceWord<R>::type;
     constexpr int L = 32 * WPP;
@@ -299,7 +301,6 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_multi_kernel(const DtwLaun
     };
     // kAhead columns of lookahead in registers (ncu: 40 % of the stall samples were long-scoreboard waits on the
     // cost loads); the step loop is unrolled by kAhead so that the ring index is a compile-time constant.
-    constexpr int kAhead = 8;
     float xq[kAhead][R];
 #pragma unroll
     for (int d = 0; d < kAhead; ++d) load_col(d + 1 - lane, xq[d]);
@@ -307,6 +308,18 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_multi_kernel(const DtwLaun
     const volatile unsigned long long *edge_in = edge + (size_t)(warp > 0 ? warp - 1 : 0) * edge_stride;
     volatile unsigned long long *edge_out = edge + (size_t)(warp < WPP - 1 ? warp : 0) * edge_stride;
     for (int s0 = 0; s0 < n_steps; s0 += kAhead) {
+      if (warp > 0 && lane == 0 && s0 + 1 <= M) {
+          // Once per group of kAhead steps: wait until the warp above has published the last column this group
+          // needs, with a back-off.  Polling every step from three spinning warps kept the shared-memory pipe busy
+          // and the leading warp (which every other warp waits for) spent a third of its time behind those loads.
+          const int need = min(M, s0 + kAhead);
+          uint32_t spins = 0;
+          while ((uint32_t)(edge_in[need - 1] >> 32) != (uint32_t)need) {
+              __nanosleep(40);
+              if (++spins > (1u << 24)) __trap();  // a protocol bug must surface as a launch failure, not a hung GPU
+          }
+      }
+      __syncwarp();
 #pragma unroll
       for (int d = 0; d < kAhead; ++d) {
         const int s = s0 + d;
@@ -314,16 +327,7 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_multi_kernel(const DtwLaun
         float up_top = __shfl_up_sync(0xffffffffu, left[R - 1], 1);
         if (lane == 0) {
             up_top = INFINITY;  // cost[0][j], j >= 1 (first warp)
-            if (warp > 0 && j <= M) {
-                // bottom row of the strip above (last lane of the previous warp), column j
-                unsigned long long w;
-                uint32_t spins = 0;
-                do {
-                    w = edge_in[j - 1];
-                    if (++spins > (1u << 26)) __trap();  // a protocol bug must surface as a launch failure, not a hung GPU
-                } while ((uint32_t)(w >> 32) != (uint32_t)j);
-                up_top = __uint_as_float((uint32_t)w);
-            }
+            if (warp > 0 && j <= M) up_top = __uint_as_float((uint32_t)edge_in[j - 1]);  // published: checked above
         }
         float xc[R];
 #pragma unroll
@@ -479,13 +483,28 @@ int64_t dtw_workspace_bytes(int n_utts, int max_rows, int max_frames) {
     return (int64_t)n_utts * (int64_t)dtw_trace_bytes(max_rows, max_frames);
 }
 
-template <int R, int WPP>
-static int launch_multi(const DtwLaunch &p, size_t smem, cudaStream_t stream) {
+template <int R, int WPP, int kAhead>
+static int launch_multi_a(const DtwLaunch &p, size_t smem, cudaStream_t stream) {
     if (smem > 48u * 1024u)
-        WCA_CUDA(cudaFuncSetAttribute(dtw_align_multi_kernel<R, WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dtw_align_multi_kernel<R, WPP><<<p.n_utts, 32 * WPP, smem, stream>>>(p);
+        WCA_CUDA(cudaFuncSetAttribute(dtw_align_multi_kernel<R, WPP, kAhead>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    dtw_align_multi_kernel<R, WPP, kAhead><<<p.n_utts, 32 * WPP, smem, stream>>>(p);
     WCA_LAUNCH_CHECK("dtw_align_multi_kernel");
     return WCA_OK;
+}
+template <int R, int WPP>
+static int launch_multi(const DtwLaunch &p, size_t smem, cudaStream_t stream) {
+    static int ahead = -1;  // experiment switch (env WCA_DTW_AHEAD: 1, 2, 4, 8)
+    if (ahead < 0) {
+        const char *e = getenv("WCA_DTW_AHEAD");
+        ahead = e ? atoi(e) : 4;
+    }
+    switch (ahead) {
+        case 1: return launch_multi_a<R, WPP, 1>(p, smem, stream);
+        case 2: return launch_multi_a<R, WPP, 2>(p, smem, stream);
+        case 8: return launch_multi_a<R, WPP, 8>(p, smem, stream);
+        default: return launch_multi_a<R, WPP, 4>(p, smem, stream);
+    }
 }
 
 template <int R>
