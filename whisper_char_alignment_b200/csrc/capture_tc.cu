@@ -242,7 +242,7 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
             tmem_ld_wait(prev);
             tmem_ld_wait(cur);
             tmem_ld_wait(next);
-#pragma unroll(W <= 3 ? 4 : 1)  // 4 = rotation period of prev/cur/next/ahead: the copies vanish
+#pragma unroll 1
             for (int b = b_lo; b < b_hi; ++b) {
                 if (b + 2 <= n_blocks) tmem_ld16_issue(trow + (uint32_t)(16 * (b + 2)), ahead);  // stays inside the accumulator
                 if (g.half > 0) {
@@ -299,7 +299,7 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
             float v[16], ahead[16];
             tmem_ld16_issue(trow + (uint32_t)(16 * b_lo), v);
             tmem_ld_wait(v);
-#pragma unroll 2
+#pragma unroll 1
             for (int b = b_lo; b < b_hi; ++b) {
                 tmem_ld16_issue(trow + (uint32_t)(16 * (b + 1)), ahead);
 #pragma unroll
