@@ -95,7 +95,7 @@ def parse():
                     help="cuBLAS fp32 GEMMs of the upstream linears: BF16x9-emulated fp32 (cuBLAS 12.9) or SIMT SGEMM")
     ap.add_argument("--profile-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed `value` region (for `ncu --profile-from-start off`)")
-    ap.add_argument("--cpu-sample", type=int, default=2, help="utterances timed for cpu_baseline (0 = skip)")
+    ap.add_argument("--cpu-sample", type=int, default=10, help="utterances timed for cpu_baseline (0 = skip)")
     args = ap.parse_args()
     if args.aggr is None:
         args.aggr = "mean" if args.workload == "ami" else "topk"
@@ -383,6 +383,20 @@ def main():
             traffic = float(rec["dram_bytes_per_launch"])
     except (OSError, KeyError, ValueError):
         pass
+    # ---- the tensor-bound kernel of the forward: unmasked attention (encoder self-attention + decoder cross-attention
+    # output), fp32-grade = three tf32 products per contraction.  Algorithmic FLOPs = 4 * n_q * n_kv * 64 per (batch, head).
+    att_calls, att_ms = kernel_ms.get("wca_full_attention", (0, 0.0))
+    att_flops = []
+    for b in batches:
+        t_max = max(len(u.tokens) for u in b)
+        att_flops.append(dims.n_audio_layer * 4.0 * len(b) * dims.n_audio_head * dims.n_audio_ctx ** 2 * 64
+                         + L * 4.0 * len(b) * H * t_max * dims.n_audio_ctx * 64)
+    att_step_flops = float(np.mean([att_flops[i] for i in used]))
+    bf16_peak = None
+    if os.path.exists(peaks_path):
+        bf16_peak = float(json.load(open(peaks_path)).get("bf16_tflops_sustained") or 0) or None
+    tf32_peak = (bf16_peak / 2.0) if bf16_peak else 1100.0 / 1.0  # dense tf32 = half the bf16 rate
+    att_useful = att_step_flops * args.steps / (att_ms / 1000.0) / 1e12 if att_ms > 0 else 0.0
     dtw_calls, dtw_ms = kernel_ms.get("wca_dtw_align", (0, 0.0))
     cells = float(np.mean([dtw_cells[i] for i in used]))
 
@@ -405,6 +419,13 @@ def main():
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": cap_bytes,
                          "avg_launch_ms": cap_ms / max(cap_calls, 1)},
+            "roofline_attention": {"kernel": "wca_full_attention (tcgen05, 3 x tf32 split for both contractions)", "bound": "tensor",
+                                   "achieved": att_useful, "unit": "TFLOP/s", "executed_tf32": 3.0 * att_useful,
+                                   "peak": tf32_peak, "frac": 3.0 * att_useful / tf32_peak if tf32_peak else None,
+                                   "peak_source": ("half of MEASURED_PEAKS.json bf16_tflops_sustained (dense tf32 runs at half the bf16 rate)"
+                                                   if bf16_peak else "fallback: nominal 1.1 PFLOP/s dense tf32"),
+                                   "calls_per_step": att_calls / max(args.steps, 1), "ms_per_step": att_ms / max(args.steps, 1),
+                                   "algorithmic_flops_per_step": att_step_flops},
             "cpu_baseline": cpu,
             "stages_ms_per_step": {k: v[1] / args.steps for k, v in sorted(kernel_ms.items())},
             "dtw_cells_per_s": cells / (dtw_ms / max(dtw_calls, 1) / 1000.0) if dtw_ms > 0 else None,
