@@ -64,7 +64,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
-template <int R>
+// kTraceSmem / kStaged are compile-time so that every trace and staged-matrix access is a plain shared-memory
+// instruction: a pointer selected at run time between shared and global memory is a generic pointer, and generic
+// LD / ST hold their registers for hundreds of cycles (ncu source page, short-scoreboard stalls).
+template <int R, bool kTraceSmem, bool kStaged>
 __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
     using Word = typename TraceWord<R>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -78,9 +81,10 @@ __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
     // shared memory: [jump buffers][traces][staged matrices], one slice per warp
     int32_t *jump_s = reinterpret_cast<int32_t *>(smem_raw) + warp * p.jump_stride;
     unsigned char *after_jump = smem_raw + (size_t)p.warps * p.jump_stride * 4;
-    Word *trace = p.trace_in_smem ? reinterpret_cast<Word *>(after_jump + (size_t)warp * p.trace_stride)
-                                  : reinterpret_cast<Word *>(p.trace_ws + (size_t)prob * p.trace_stride);
-    float *xs = reinterpret_cast<float *>(after_jump + (p.trace_in_smem ? (size_t)p.warps * p.trace_stride : 0)) +
+    Word *trace;
+    if constexpr (kTraceSmem) trace = reinterpret_cast<Word *>(after_jump + (size_t)warp * p.trace_stride);
+    else trace = reinterpret_cast<Word *>(p.trace_ws + (size_t)prob * p.trace_stride);
+    float *xs = reinterpret_cast<float *>(after_jump + (kTraceSmem ? (size_t)p.warps * p.trace_stride : 0)) +
                 (size_t)warp * p.xs_floats;
     if (N <= 0 || M <= 0) {
         if (lane == 0 && p.path_len) p.path_len[prob] = 0;
@@ -90,7 +94,7 @@ __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
 
     // ---- stage the cost matrix (coalesced, sign applied once) -----------------------------------
     const float *xg = p.matrix + u.matrix_off;
-    const bool staged = p.staged != 0;
+    constexpr bool staged = kStaged;
     if (staged) {
         // same misalignment in shared memory as in global memory, so the body moves 16 bytes per lane and load
         const int total = N * M;
@@ -110,7 +114,6 @@ __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
         for (int e = head + 4 * body + lane; e < total; e += 32) xs[e] = p.negate ? -ld_stream(xg + e) : ld_stream(xg + e);
         __syncwarp();
     }
-    const float *x = staged ? xs : xg;
     const bool flip = p.negate && !staged;
 
     // ---- forward sweep: lane l handles table rows l*R+1 .. l*R+R, column j = step - l + 1 ------
@@ -139,7 +142,10 @@ __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
         for (int r = 0; r < R; ++r) {
             const int row = row0 + r;
             float v = 0.f;
-            if (row < N && j >= 1 && j <= M) v = x[(int64_t)row * M + (j - 1)];
+            if (row < N && j >= 1 && j <= M) {
+                if constexpr (kStaged) v = xs[row * M + (j - 1)];
+                else v = xg[(int64_t)row * M + (j - 1)];
+            }
             dst[r] = v;
         }
     };
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
 // arrives by __shfl_up as before; between warps lane 31 of warp w publishes the bottom row of its strip,
 // column by column, in a shared line `edge[w][j]` followed by a progress counter, and lane 0 of warp w + 1
 // (which runs 32 steps behind by construction) polls the counter: no block barrier on the recurrence.
-template <int R, int WPP, int kAhead>
+template <int R, int WPP, int kAhead, bool kTraceSmem>
 __global__ void __launch_bounds__(32 * WPP) dtw_align_multi_kernel(const DtwLaunch p) {
     using Word = typename TraceWord<R>::type;
     constexpr int L = 32 * WPP;
@@ -272,9 +278,9 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_multi_kernel(const DtwLaun
     // producer needs no fence and the consumer polls the very word it wants (tag 0 = not yet written)
     unsigned long long *edge = reinterpret_cast<unsigned long long *>(smem_raw + 64 + (size_t)p.jump_stride * 4);
     const int edge_stride = (int)(p.xs_floats / 2 / (WPP > 1 ? WPP - 1 : 1));
-    Word *trace = p.trace_in_smem
-                      ? reinterpret_cast<Word *>(smem_raw + 64 + (size_t)p.jump_stride * 4 + (size_t)p.xs_floats * 4)
-                      : reinterpret_cast<Word *>(p.trace_ws + (size_t)prob * p.trace_stride);
+    Word *trace;
+    if constexpr (kTraceSmem) trace = reinterpret_cast<Word *>(smem_raw + 64 + (size_t)p.jump_stride * 4 + (size_t)p.xs_floats * 4);
+    else trace = reinterpret_cast<Word *>(p.trace_ws + (size_t)prob * p.trace_stride);
     if (N <= 0 || M <= 0) {
         if (g == 0 && p.path_len) p.path_len[prob] = 0;
         return;
@@ -444,6 +450,9 @@ static size_t dtw_trace_bytes(int max_rows, int max_frames) {
 constexpr size_t kSmemBudget = 227u * 1024u;
 
 // Shared-memory plan for a launch: problems per CTA, whether the trace, the staged matrix or the prefetch ring fit.
+// The per-lane cp.async ring (prefetch_col / take_col) measured no better than plain loads one column ahead
+// (64 x (401 x 1500): 1.9 ms with it, 1.5 ms without): the sweep is not bound by load latency.  Kept behind this switch.
+constexpr bool kUseRing = false;
 struct DtwPlan {
     int warps, trace_in_smem, staged, ring, xs_floats;
     size_t smem;
@@ -461,7 +470,7 @@ static DtwPlan dtw_plan(int max_rows, int max_frames) {
         }
     }
     for (int warps = 4; warps >= 1; warps >>= 1) {
-        if (warps * (jump + trace + ring) <= kSmemBudget) {
+        if (kUseRing && warps * (jump + trace + ring) <= kSmemBudget) {
             pl = {warps, 1, 0, 1, (int)(ring / 4), warps * (jump + trace + ring)};
             return pl;
         }
@@ -472,7 +481,8 @@ static DtwPlan dtw_plan(int max_rows, int max_frames) {
             return pl;
         }
     }
-    pl = {4, 0, 0, 1, (int)(ring / 4), 4 * (jump + ring)};  // trace in the global workspace
+    if (kUseRing) pl = {4, 0, 0, 1, (int)(ring / 4), 4 * (jump + ring)};  // trace in the global workspace
+    else pl = {4, 0, 0, 0, 0, 4 * jump};
     return pl;
 }
 
@@ -483,38 +493,40 @@ int64_t dtw_workspace_bytes(int n_utts, int max_rows, int max_frames) {
     return (int64_t)n_utts * (int64_t)dtw_trace_bytes(max_rows, max_frames);
 }
 
-template <int R, int WPP, int kAhead>
-static int launch_multi_a(const DtwLaunch &p, size_t smem, cudaStream_t stream) {
+template <int R, int WPP, int kAhead, bool kTraceSmem>
+static int launch_multi_s(const DtwLaunch &p, size_t smem, cudaStream_t stream) {
     if (smem > 48u * 1024u)
-        WCA_CUDA(cudaFuncSetAttribute(dtw_align_multi_kernel<R, WPP, kAhead>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-    dtw_align_multi_kernel<R, WPP, kAhead><<<p.n_utts, 32 * WPP, smem, stream>>>(p);
+        WCA_CUDA(cudaFuncSetAttribute(dtw_align_multi_kernel<R, WPP, kAhead, kTraceSmem>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dtw_align_multi_kernel<R, WPP, kAhead, kTraceSmem><<<p.n_utts, 32 * WPP, smem, stream>>>(p);
     WCA_LAUNCH_CHECK("dtw_align_multi_kernel");
     return WCA_OK;
 }
+template <int R, int WPP, int kAhead>
+static int launch_multi_a(const DtwLaunch &p, size_t smem, cudaStream_t stream) {
+    return p.trace_in_smem ? launch_multi_s<R, WPP, kAhead, true>(p, smem, stream)
+                           : launch_multi_s<R, WPP, kAhead, false>(p, smem, stream);
+}
 template <int R, int WPP>
 static int launch_multi(const DtwLaunch &p, size_t smem, cudaStream_t stream) {
-    static int ahead = -1;  // experiment switch (env WCA_DTW_AHEAD: 1, 2, 4, 8)
-    if (ahead < 0) {
-        const char *e = getenv("WCA_DTW_AHEAD");
-        ahead = e ? atoi(e) : 4;
-    }
-    switch (ahead) {
-        case 1: return launch_multi_a<R, WPP, 1>(p, smem, stream);
-        case 2: return launch_multi_a<R, WPP, 2>(p, smem, stream);
-        case 8: return launch_multi_a<R, WPP, 8>(p, smem, stream);
-        default: return launch_multi_a<R, WPP, 4>(p, smem, stream);
-    }
+    return launch_multi_a<R, WPP, 4>(p, smem, stream);  // 4 columns of lookahead (1..8 measured the same)
 }
 
-template <int R>
-static int launch_r(const DtwLaunch &p, size_t smem, cudaStream_t stream) {
+template <int R, bool kTraceSmem, bool kStaged>
+static int launch_rs(const DtwLaunch &p, size_t smem, cudaStream_t stream) {
     if (smem > 48u * 1024u)
-        WCA_CUDA(cudaFuncSetAttribute(dtw_align_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        WCA_CUDA(cudaFuncSetAttribute(dtw_align_kernel<R, kTraceSmem, kStaged>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
     const int grid = (p.n_utts + p.warps - 1) / p.warps;
-    dtw_align_kernel<R><<<grid, p.warps * 32, smem, stream>>>(p);
+    dtw_align_kernel<R, kTraceSmem, kStaged><<<grid, p.warps * 32, smem, stream>>>(p);
     WCA_LAUNCH_CHECK("dtw_align_kernel");
     return WCA_OK;
+}
+template <int R>
+static int launch_r(const DtwLaunch &p, size_t smem, cudaStream_t stream) {
+    if (p.trace_in_smem && p.staged) return launch_rs<R, true, true>(p, smem, stream);
+    if (p.trace_in_smem) return launch_rs<R, true, false>(p, smem, stream);
+    return launch_rs<R, false, false>(p, smem, stream);
 }
 
 int launch_dtw_align(const float *d_matrix, const wca_utt_t *d_utts, int n_utts, int max_rows, int max_frames,
