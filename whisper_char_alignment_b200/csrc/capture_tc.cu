@@ -73,9 +73,11 @@ constexpr int kOffTile = kOffKLo + kKBytes;                     // 8 epilogue wa
 constexpr int kOffStat = kOffTile + 8 * 32 * kTilePitch * 4;    // smax[2][128], ssum[2][128]
 constexpr int kOffBar = kOffStat + 4 * kRows * 4;
 enum Bar {
-    kOpFull = 0,                 // TMA -> splitters (transaction bytes): Q tile + K slab landed
-    kOpReady = kOpFull + 1,      // splitters -> MMA issuer: lo twins written
-    kOpFree = kOpReady + 1,      // MMA (tcgen05.commit) -> TMA producer: operands no longer read
+    kKFull = 0,                  // TMA -> splitters (transaction bytes): K slab landed
+    kQFull = kKFull + 1,         // ... Q tile landed
+    kOpReady = kQFull + 1,       // splitters -> MMA issuer: lo twins written
+    kKFree = kOpReady + 1,       // MMA (tcgen05.commit after the two passes that read K_hi) -> TMA producer: K_hi may be refilled
+    kOpFree = kKFree + 1,        // MMA (tcgen05.commit after the last pass) -> producer (Q_hi) and splitters (lo twins)
     kAccFull = kOpFree + 1,
     kAccEmpty = kAccFull + 2,
     kXMax = kAccEmpty + 2,
@@ -392,8 +394,10 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
 
     // ---- setup ------------------------------------------------------------------------
     if (tid == 0) {
-        mbar_init(bar(kOpFull), 1);
+        mbar_init(bar(kKFull), 1);
+        mbar_init(bar(kQFull), 1);
         mbar_init(bar(kOpReady), kSplitThreads);
+        mbar_init(bar(kKFree), 1);
         mbar_init(bar(kOpFree), 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar(kAccFull + i), 1);
@@ -421,21 +425,29 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
         for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
             const Geo g = decode_tile<W>(a, tile, crank, csize);
             if (!g.live || g.n_own == 0) continue;
-            mbar_wait(bar(kOpFree), (n_tile & 1u) ^ 1u);  // MMAs of the previous tile no longer read Q / K (first lap passes)
+            // K_hi is refilled as soon as the two MMA passes that read it have run (a third of the MMA time and the whole
+            // drain earlier than the last pass), Q_hi once all of them have: the K load -- 60 % of the bytes -- is then
+            // already in shared memory when the splitters are allowed to touch the lo twins.
+            const bool upper = g.dup || g.rows_valid > kStageRows;
+            mbar_wait(bar(kKFree), (n_tile & 1u) ^ 1u);  // first lap passes
+            if (lane == 0) {
+                mbar_expect_tx(bar(kKFull), g.n_chunks * 2 * kBoxBytes);  // boxes are always full: rows past the matrix end read as zero
+                const CUtensorMap *kmap = &maps.k[g.n_chunks - 1][g.layer];   // box = n_chunks * 64 frames
+                for (int half = 0; half < 2; ++half)
+                    tma_load_box(k_hi + half * kKHalfBytes, kmap, g.col0 + half * kBoxCols, g.krow0 + g.m0, bar(kKFull));
+            }
+            __syncwarp();
+            mbar_wait(bar(kOpFree), (n_tile & 1u) ^ 1u);  // MMAs of the previous tile no longer read Q
             if (lane == 0) {
                 // Q rows 64..127: the next 64 token rows, or (Geo::dup) a second copy of rows 0..63; with <= 64
                 // rows and no mirroring the upper half is left as it is (nobody reads those lanes)
-                const bool upper = g.dup || g.rows_valid > kStageRows;
-                // boxes are always full: rows past the matrix end read as zero
-                mbar_expect_tx(bar(kOpFull), (upper ? kQBytes : kQBytes / 2) + g.n_chunks * 2 * kBoxBytes);
-                const CUtensorMap *kmap = &maps.k[g.n_chunks - 1][g.layer];   // box = n_chunks * 64 frames
+                mbar_expect_tx(bar(kQFull), upper ? kQBytes : kQBytes / 2);
                 const CUtensorMap *qmap = &maps.q[(upper && !g.dup) ? 1 : 0][g.layer];
                 for (int half = 0; half < 2; ++half) {
-                    tma_load_box(k_hi + half * kKHalfBytes, kmap, g.col0 + half * kBoxCols, g.krow0 + g.m0, bar(kOpFull));
-                    tma_load_box(q_hi + half * kQHalfBytes, qmap, g.col0 + half * kBoxCols, g.qrow0, bar(kOpFull));
+                    tma_load_box(q_hi + half * kQHalfBytes, qmap, g.col0 + half * kBoxCols, g.qrow0, bar(kQFull));
                     if (g.dup)
                         tma_load_box(q_hi + half * kQHalfBytes + kBoxBytes, qmap, g.col0 + half * kBoxCols, g.qrow0,
-                                     bar(kOpFull));
+                                     bar(kQFull));
                 }
             }
             __syncwarp();
@@ -488,16 +500,17 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
             const int n_cols = min(kAccCols, (g.n_mma + 15) & ~15);  // UMMA N: multiple of 16
             const uint32_t idesc = instr_desc_tf32(kRows, n_cols);
             const uint32_t d = tm + buf * kAccCols + (uint32_t)g.mcol0;
-            // small terms first: lo*hi, hi*lo, then hi*hi
+            // the two passes that read K_hi first (lo*hi, hi*hi), so that K_hi can be refilled while hi*lo still runs
 #pragma unroll
             for (int pass = 0; pass < 3; ++pass) {
                 const uint64_t da = pass == 0 ? da_lo : da_hi;
-                const uint64_t db = pass == 1 ? db_lo : db_hi;
+                const uint64_t db = pass == 2 ? db_lo : db_hi;
 #pragma unroll
                 for (int ks = 0; ks < kHeadDim / 8; ++ks)
                     umma_tf32_ss_if(d, da + (uint64_t)(((ks >> 2) * kQHalfBytes + (ks & 3) * 32) >> 4),
                                     db + (uint64_t)(((ks >> 2) * kKHalfBytes + (ks & 3) * 32) >> 4), idesc, (pass | ks) != 0,
                                     elected);
+                if (pass == 1) umma_commit_if(bar(kKFree), elected);
             }
             umma_commit_if(bar(kOpFree), elected);
             umma_commit_if(bar(kAccFull + buf), elected);
@@ -512,13 +525,15 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
         for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
             const Geo g = decode_tile<W>(a, tile, crank, csize);
             if (!g.live || g.n_own == 0) continue;
-            mbar_wait(bar(kOpFull), n_tile & 1u);
+            mbar_wait(bar(kOpFree), (n_tile & 1u) ^ 1u);  // the previous tile's MMAs no longer read the lo twins (first lap passes)
+            mbar_wait(bar(kKFull), n_tile & 1u);
             stamp(tr, n_tile, kEvSplFull);
             for (int half = 0; half < 2; ++half)
                 for (int c = 0; c < g.n_chunks; ++c)
                     split_lo<kBoxBytes>(smem + kOffKHi + half * kKHalfBytes + c * kBoxBytes,
                                         smem + kOffKLo + half * kKHalfBytes + c * kBoxBytes, t);
             stamp(tr, n_tile, kEvSplK0Done);
+            mbar_wait(bar(kQFull), n_tile & 1u);
             split_lo<kQBytes>(smem + kOffQHi, smem + kOffQLo, t);
             fence_proxy_async_smem();  // generic-proxy stores must be visible to the tensor core's async proxy
             mbar_arrive(bar(kOpReady));
