@@ -70,8 +70,8 @@ constexpr int kOffQLo = kOffQHi + kQBytes;
 constexpr int kOffKHi = kOffQLo + kQBytes;
 constexpr int kOffKLo = kOffKHi + kKBytes;
 constexpr int kOffTile = kOffKLo + kKBytes;                     // 8 epilogue warps x 32 x 17 floats
-constexpr int kOffStat = kOffTile + 8 * 32 * kTilePitch * 4;    // smax[2][128], ssum[2][128]
-constexpr int kOffBar = kOffStat + 4 * kRows * 4;
+constexpr int kOffStat = kOffTile + 8 * 32 * kTilePitch * 4;    // [group][tile parity][m | sum][128]
+constexpr int kOffBar = kOffStat + 8 * kRows * 4;
 enum Bar {
     kKFull = 0,                  // TMA -> splitters (transaction bytes): K slab landed
     kQFull = kKFull + 1,         // ... Q tile landed
@@ -217,14 +217,11 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
     const bool sweep = rows_live && b_lo < b_hi;
     const uint32_t trow = acc + ((uint32_t)(ewarp * 32) << 16) + kOwnCol0;  // own frame 0 of this lane quarter
     const int tail = g.n_own - 16 * (n_blocks - 1);  // valid columns of the last block (1..16)
-    float *smax = reinterpret_cast<float *>(smem + kOffStat) + grp * kRows;
-    float *ssum = reinterpret_cast<float *>(smem + kOffStat) + (2 + grp) * kRows;
+    float *sstat = reinterpret_cast<float *>(smem + kOffStat) + grp * 4 * kRows;  // [tile parity][m | sum][128]
     const uint32_t bar_xmax = smem_u32(smem + kOffBar) + 8u * (kXMax + grp);
-    const uint32_t bar_xsum = smem_u32(smem + kOffBar) + 8u * (kXSum + grp);
 
     float inv_sum = a.s;  // raw-logit mode: only the 2^-3 of the operand scaling is applied
     if (!a.raw_logits) {
-        float row_max = -INFINITY;
         if (rows_live && g.half > 0) {
             {
                 // materialise the reflect padding in TMEM: frame -i <- frame i, frame F-1+i <- frame F-1-i
@@ -235,8 +232,14 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
                 tmem_wait_st();
             }
         }
+        // Sweep A+B fused: median filter, * qk_scale, and e = 2^(y - m) against a LAZY per-thread reference m
+        // (the maximum of the thread's first block; it only moves when a later block exceeds it by 2^32, and the
+        // few blocks already written are then rescaled in place), with the running sum.  One pass over tensor
+        // memory instead of two and a single exchange of (m, sum) pairs between column halves / cluster ranks.
+        const float kLog2e = 1.4426950408889634f;
+        const float scale2 = a.qk_scale * kLog2e;
+        float m2 = -INFINITY, row_sum = 0.f;
         if (sweep) {
-            // sweep A: median filter in place, * qk_scale, running max; the load of block b+2 is in flight
             float prev[16], cur[16], next[16], ahead[16], med[16];
             tmem_ld16_issue(trow + (uint32_t)(16 * (b_lo - 1) + 16) - 16u, prev);
             tmem_ld16_issue(trow + (uint32_t)(16 * b_lo), cur);
@@ -253,15 +256,32 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
 #pragma unroll
                     for (int i = 0; i < 16; ++i) med[i] = cur[i];
                 }
+                const int n_ok = b + 1 < n_blocks ? 16 : tail;
+                float bmax = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) med[i] *= a.qk_scale;
-                if (b + 1 < n_blocks) {
+                for (int i = 0; i < 16; ++i) {
+                    med[i] *= scale2;
+                    if (i < n_ok) bmax = fmaxf(bmax, med[i]);
+                }
+                if (b == b_lo) m2 = bmax;
+                const bool need = bmax > m2 + 32.f;
+                if (__any_sync(0xffffffffu, need)) {  // rare: move the reference, rescale what is already stored
+                    const float f = need ? ex2_approx(m2 - bmax) : 1.f;
+                    if (need) m2 = bmax;
+                    row_sum *= f;
+                    for (int bb = b_lo; bb < b; ++bb) {
+                        float t[16];
+                        tmem_ld16_issue(trow + (uint32_t)(16 * bb), t);
+                        tmem_ld_wait(t);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) row_max = fmaxf(row_max, med[i]);
-                } else {
+                        for (int i = 0; i < 16; ++i) t[i] *= f;
+                        tmem_st16(trow + (uint32_t)(16 * bb), t);
+                    }
+                }
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (i < tail) row_max = fmaxf(row_max, med[i]);
+                for (int i = 0; i < 16; ++i) {
+                    med[i] = ex2_approx(med[i] - m2);
+                    if (i < n_ok) row_sum += med[i];
                 }
                 tmem_st16(trow + (uint32_t)(16 * b), med);
                 tmem_ld_wait(ahead);
@@ -275,69 +295,38 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
             tmem_wait_st();
         }
         stamp(tr, seq, kEvEpiA);
-        float gmax = row_max;
-        if (g.dup) {  // combine the two column halves of a mirrored tile
-            smax[ewarp * 32 + lane] = row_max;
+        stamp(tr, seq, kEvEpiXMax);
+        stamp(tr, seq, kEvEpiB);
+        // (m, sum) of the other column half (mirrored tiles) and of the other cluster ranks; the statistics
+        // buffers alternate with the tile parity so that nobody overwrites a pair a slower peer still reads
+        float *smax = sstat + (x_parity * 2 + 0) * kRows;
+        float *ssum = sstat + (x_parity * 2 + 1) * kRows;
+        float gmax = m2, gsum = row_sum;
+        if (g.dup) {
+            smax[ewarp * 32 + lane] = m2;
+            ssum[ewarp * 32 + lane] = row_sum;
             named_bar_sync(1 + grp, kEpiThreads);
-            gmax = fmaxf(row_max, smax[(ewarp ^ 2) * 32 + lane]);
+            const float pm = smax[(ewarp ^ 2) * 32 + lane], ps = ssum[(ewarp ^ 2) * 32 + lane];
+            gmax = fmaxf(m2, pm);
+            gsum = (m2 > -INFINITY ? row_sum * ex2_approx(m2 - gmax) : 0.f) + (pm > -INFINITY ? ps * ex2_approx(pm - gmax) : 0.f);
         }
         if (csize > 1) {
-            // exchange the row maxima across the cluster (every CTA takes part, even with no own frames)
-            smax[row] = row_ok ? row_max : -INFINITY;
+            // every CTA of the cluster takes part, even with no own frames
+            smax[row] = row_ok ? m2 : -INFINITY;
+            ssum[row] = row_ok ? row_sum : 0.f;
             named_bar_sync(1 + grp, kEpiThreads);
             if (row == 0)
                 for (uint32_t r = 0; r < csize; ++r) mbar_arrive_remote(bar_xmax, r);
             mbar_wait_cluster(bar_xmax, x_parity);
             gmax = -INFINITY;
             for (uint32_t r = 0; r < csize; ++r) gmax = fmaxf(gmax, ld_dsmem_f32(&smax[row], r));
-        }
-        stamp(tr, seq, kEvEpiXMax);
-
-        float row_sum = 0.f;
-        if (sweep) {
-            // sweep B: e = exp(x - max) in place, running sum; one block of loads in flight
-            const float kLog2e = 1.4426950408889634f;
-            const float shift = gmax * kLog2e;
-            float v[16], ahead[16];
-            tmem_ld16_issue(trow + (uint32_t)(16 * b_lo), v);
-            tmem_ld_wait(v);
-#pragma unroll 1
-            for (int b = b_lo; b < b_hi; ++b) {
-                tmem_ld16_issue(trow + (uint32_t)(16 * (b + 1)), ahead);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = ex2_approx(fmaf(v[i], kLog2e, -shift));
-                if (b + 1 < n_blocks) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) row_sum += v[i];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (i < tail) row_sum += v[i];
-                }
-                tmem_st16(trow + (uint32_t)(16 * b), v);
-                tmem_ld_wait(ahead);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = ahead[i];
-            }
-            tmem_wait_st();
-        }
-        stamp(tr, seq, kEvEpiB);
-        float gsum = row_sum;
-        if (g.dup) {
-            ssum[ewarp * 32 + lane] = row_sum;
-            named_bar_sync(1 + grp, kEpiThreads);
-            gsum = row_sum + ssum[(ewarp ^ 2) * 32 + lane];
-        }
-        if (csize > 1) {
-            ssum[row] = row_ok ? row_sum : 0.f;
-            named_bar_sync(1 + grp, kEpiThreads);
-            if (row == 0)
-                for (uint32_t r = 0; r < csize; ++r) mbar_arrive_remote(bar_xsum, r);
-            mbar_wait_cluster(bar_xsum, x_parity);
             gsum = 0.f;
-            for (uint32_t r = 0; r < csize; ++r) gsum += ld_dsmem_f32(&ssum[row], r);
+            for (uint32_t r = 0; r < csize; ++r) {
+                const float mr = ld_dsmem_f32(&smax[row], r);
+                if (mr > -INFINITY) gsum += ld_dsmem_f32(&ssum[row], r) * ex2_approx(mr - gmax);
+            }
         }
-        inv_sum = 1.f / gsum;
+        inv_sum = (m2 > -INFINITY ? ex2_approx(m2 - gmax) : 0.f) / gsum;  // this thread's e values are relative to its own m
         stamp(tr, seq, kEvEpiXSum);
     }
 
