@@ -7,7 +7,7 @@ from whisper_char_alignment_b200 import _cabi
 shape = sys.argv[1] if len(sys.argv) > 1 else "timit"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 simt = len(sys.argv) > 3 and sys.argv[3] == "simt"
-reps = 3
+reps = int(os.environ.get("WCA_REPS", "20"))
 dev = torch.device("cuda:0")
 L, H, D, n_ctx = 24, 16, 64, 1500
 rng = np.random.default_rng(0)
@@ -24,7 +24,7 @@ for b in range(B):
     recs[b]["n_tokens"], recs[b]["n_frames"] = Ts[b], Fs[b]
     recs[b]["q_row0"], recs[b]["k_row0"], recs[b]["ws_off"] = b * t_max, b * n_ctx, off
     off += L * H * int(Ts[b]) * int(Fs[b])
-flags = _cabi.WCA_CAPTURE_FORCE_SIMT if simt else 0
+flags = (_cabi.WCA_CAPTURE_FORCE_SIMT if simt else 0) | int(os.environ.get("WCA_DBG", "0"), 0)  # bits 8..: experiment switches
 from whisper_char_alignment_b200.timing import _cluster_bucket
 buckets = {}
 for b in range(B):
@@ -38,18 +38,18 @@ def capture():
                                 3, 1.0, ws, flags)
 
 bytes_alg = 4 * off + sum(4 * L * (int(t) + int(f)) * H * D for t, f in zip(Ts, Fs))
-for _ in range(2):
+for _ in range(10):
     capture()
 torch.cuda.synchronize()
 a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-tot = 0.0
+times = []
 for _ in range(reps):
     flush.zero_()
     a.record()
     capture()
     b_.record(); torch.cuda.synchronize()
-    tot += a.elapsed_time(b_)
-ms = tot / reps
-print(f"{shape} B={B} {'simt+filter' if simt else 'tcgen05'}: {ms:.3f} ms/batch ({len(launches)} launch(es)), algorithmic {bytes_alg/1e6:.1f} MB -> {bytes_alg/ms/1e6:.1f} GB/s "
+    times.append(a.elapsed_time(b_))
+ms = float(np.median(times))
+print(f"{shape} B={B} {'simt+filter' if simt else 'tcgen05'} dbg={flags:#x}: median {ms:.3f} (min {min(times):.3f}) ms/batch ({len(launches)} launch(es)), algorithmic {bytes_alg/1e6:.1f} MB -> {bytes_alg/ms/1e6:.1f} GB/s "
       f"({bytes_alg/ms/1e6/6548.5*100:.1f}% of measured HBM peak)")

@@ -75,8 +75,9 @@ constexpr int kOffBar = kOffStat + 8 * kRows * 4;
 enum Bar {
     kKFull = 0,                  // TMA -> splitters (transaction bytes): K slab landed
     kQFull = kKFull + 1,         // ... Q tile landed
-    kOpReady = kQFull + 1,       // splitters -> MMA issuer: lo twins written
-    kKFree = kOpReady + 1,       // MMA (tcgen05.commit after the two passes that read K_hi) -> TMA producer: K_hi may be refilled
+    kKLoReady = kQFull + 1,      // splitters -> MMA issuer: K lo twin written
+    kQLoReady = kKLoReady + 1,   // splitters -> MMA issuer: Q lo twin written
+    kKFree = kQLoReady + 1,      // MMA (tcgen05.commit after the two passes that read K_hi, once the K twin is written) -> TMA producer: K_hi may be refilled
     kOpFree = kKFree + 1,        // MMA (tcgen05.commit after the last pass) -> producer (Q_hi) and splitters (lo twins)
     kAccFull = kOpFree + 1,
     kAccEmpty = kAccFull + 2,
@@ -177,26 +178,114 @@ __device__ __forceinline__ void split_lo(const unsigned char *hi, unsigned char 
         dst[it * kSplitThreads + t] = make_float4(tf32_lo(v[it].x), tf32_lo(v[it].y), tf32_lo(v[it].z), tf32_lo(v[it].w));
 }
 
-// Sliding median over a 16-column block with its neighbour blocks; every index is a compile
-// time constant after unrolling, so the window lives in registers.
+// Sliding median over a 16-column block; every index is a compile time constant after unrolling, so the
+// window lives in registers.  `ptail` = the last W/2 columns of the previous block, `next` = the next block.
 template <int W>
-__device__ __forceinline__ void median_block(const float (&prev)[16], const float (&cur)[16], const float (&next)[16],
-                                             float (&out)[16]) {
+struct Tail {
+    static constexpr int kLen = W / 2 > 0 ? W / 2 : 1;
+};
+template <int W>
+__device__ __forceinline__ void median_block(const float (&ptail)[Tail<W>::kLen], const float (&cur)[16],
+                                             const float (&next)[16], float (&out)[16]) {
     constexpr int half = W / 2;
+    if constexpr (W == 1) {
 #pragma unroll
-    for (int pos = 0; pos < 16; ++pos) {
-        if constexpr (W == 1) {
-            out[pos] = cur[pos];
-        } else {
+        for (int pos = 0; pos < 16; ++pos) out[pos] = cur[pos];
+    } else if constexpr (W == 3) {
+        // med(a, b, c) = max(min(a, b), min(max(a, b), c)): the (min, max) of the pair (2k, 2k+1) serves both of
+        // its positions (with the left / the right neighbour): 3 instead of 5 min/max per column, still exact
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float lo = fminf(cur[2 * k], cur[2 * k + 1]);
+            const float hi = fmaxf(cur[2 * k], cur[2 * k + 1]);
+            const float left = k == 0 ? ptail[0] : cur[2 * k - 1];
+            const float right = k == 7 ? next[0] : cur[2 * k + 2];
+            out[2 * k] = fmaxf(lo, fminf(hi, left));
+            out[2 * k + 1] = fmaxf(lo, fminf(hi, right));
+        }
+    } else {
+#pragma unroll
+        for (int pos = 0; pos < 16; ++pos) {
             float win[W];
 #pragma unroll
             for (int j = 0; j < W; ++j) {
-                const int idx = 16 + pos - half + j;  // position in prev | cur | next
-                win[j] = idx < 16 ? prev[idx] : (idx < 32 ? cur[idx - 16] : next[idx - 32]);
+                const int idx = pos - half + j;  // relative to cur[0]
+                win[j] = idx < 0 ? ptail[half + idx] : (idx < 16 ? cur[idx] : next[idx - 16]);
             }
             out[pos] = median_regs<W>(win);
         }
     }
+}
+
+// One 16-column block of the fused filter / exponential sweep (epilogue_tile, sweep A+B).  `cur` is dead once
+// the filter has run, so the block after next is loaded straight into its registers: the caller alternates the
+// roles of the two buffers instead of moving 32 registers per block.
+struct RowStats {
+    float m2, row_sum;
+};
+template <int W>
+__device__ __forceinline__ void filter_exp_block(uint32_t trow, int b, int b_lo, int n_blocks, int tail, bool filter,
+                                                 float scale2, float (&ptail)[Tail<W>::kLen], float (&cur)[16],
+                                                 float (&next)[16], RowStats &st) {
+    float med[16];
+    median_block<W>(ptail, cur, next, med);
+    if (W > 1 && !filter) {  // rows of at most W/2 frames are not filtered (as upstream): rare, kept off the hot path
+#pragma unroll
+        for (int i = 0; i < 16; ++i) med[i] = cur[i];
+    }
+    if constexpr (W > 1) {
+#pragma unroll
+        for (int j = 0; j < W / 2; ++j) ptail[j] = cur[16 - W / 2 + j];
+    }
+    if (b + 2 <= n_blocks) tmem_ld16_issue(trow + (uint32_t)(16 * (b + 2)), cur);  // stays inside the accumulator
+    const int n_ok = b + 1 < n_blocks ? 16 : tail;
+    if (n_ok < 16) {  // last block: columns past the row end must not win the maximum
+#pragma unroll
+        for (int i = 1; i < 16; ++i)
+            if (i >= n_ok) med[i] = med[0];
+    }
+    // extreme of the block in the direction of the scale, then ONE multiply: y = med * scale2 is monotone
+    float ext;
+    if (scale2 >= 0.f) {
+        ext = fmaxf(fmaxf(med[0], med[1]), med[2]);
+#pragma unroll
+        for (int i = 3; i < 15; i += 2) ext = fmaxf(fmaxf(ext, med[i]), med[i + 1]);
+        ext = fmaxf(ext, med[15]);
+    } else {
+        ext = fminf(fminf(med[0], med[1]), med[2]);
+#pragma unroll
+        for (int i = 3; i < 15; i += 2) ext = fminf(fminf(ext, med[i]), med[i + 1]);
+        ext = fminf(ext, med[15]);
+    }
+    const float bmax = ext * scale2;
+    if (b == b_lo) st.m2 = bmax;
+    const bool need = bmax > st.m2 + 32.f;
+    if (__any_sync(0xffffffffu, need)) {  // rare: move the reference, rescale what is already stored
+        const float f = need ? ex2_approx(st.m2 - bmax) : 1.f;
+        if (need) st.m2 = bmax;
+        st.row_sum *= f;
+#pragma unroll 1
+        for (int bb = b_lo; bb < b; ++bb) {
+            float t[16];
+            tmem_ld16_issue(trow + (uint32_t)(16 * bb), t);
+            tmem_ld_wait(t);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t[i] *= f;
+            tmem_st16(trow + (uint32_t)(16 * bb), t);
+        }
+    }
+    const float neg_m2 = -st.m2;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) med[i] = ex2_approx(__fmaf_rn(med[i], scale2, neg_m2));
+    if (n_ok < 16) {
+#pragma unroll
+        for (int i = 1; i < 16; ++i)
+            if (i >= n_ok) med[i] = 0.f;
+    }
+    st.row_sum += ((med[0] + med[1]) + (med[2] + med[3])) + ((med[4] + med[5]) + (med[6] + med[7])) +
+                  (((med[8] + med[9]) + (med[10] + med[11])) + ((med[12] + med[13]) + (med[14] + med[15])));
+    tmem_st16(trow + (uint32_t)(16 * b), med);
+    tmem_ld_wait(cur);  // the block after next has landed (also orders the loads of the rescale path)
 }
 
 // The three sweeps of one tile by one epilogue warpgroup (thread <-> token row).
@@ -238,62 +327,29 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
         // memory instead of two and a single exchange of (m, sum) pairs between column halves / cluster ranks.
         const float kLog2e = 1.4426950408889634f;
         const float scale2 = a.qk_scale * kLog2e;
-        float m2 = -INFINITY, row_sum = 0.f;
+        RowStats st{-INFINITY, 0.f};
         if (sweep) {
-            float prev[16], cur[16], next[16], ahead[16], med[16];
-            tmem_ld16_issue(trow + (uint32_t)(16 * (b_lo - 1) + 16) - 16u, prev);
-            tmem_ld16_issue(trow + (uint32_t)(16 * b_lo), cur);
-            tmem_ld16_issue(trow + (uint32_t)(16 * (b_lo + 1)), next);
-            tmem_ld_wait(prev);
-            tmem_ld_wait(cur);
-            tmem_ld_wait(next);
+            float ptail[Tail<W>::kLen], bufa[16], bufb[16];
+            {
+                float prev[16];
+                tmem_ld16_issue(trow + (uint32_t)(16 * b_lo) - 16u, prev);
+                tmem_ld16_issue(trow + (uint32_t)(16 * b_lo), bufa);
+                tmem_ld16_issue(trow + (uint32_t)(16 * (b_lo + 1)), bufb);
+                tmem_ld_wait(prev);
+                tmem_ld_wait(bufa);
+                tmem_ld_wait(bufb);
+#pragma unroll
+                for (int j = 0; j < Tail<W>::kLen; ++j) ptail[j] = prev[16 - Tail<W>::kLen + j];
+            }
 #pragma unroll 1
-            for (int b = b_lo; b < b_hi; ++b) {
-                if (b + 2 <= n_blocks) tmem_ld16_issue(trow + (uint32_t)(16 * (b + 2)), ahead);  // stays inside the accumulator
-                if (g.half > 0) {
-                    median_block<W>(prev, cur, next, med);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) med[i] = cur[i];
-                }
-                const int n_ok = b + 1 < n_blocks ? 16 : tail;
-                float bmax = -INFINITY;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    med[i] *= scale2;
-                    if (i < n_ok) bmax = fmaxf(bmax, med[i]);
-                }
-                if (b == b_lo) m2 = bmax;
-                const bool need = bmax > m2 + 32.f;
-                if (__any_sync(0xffffffffu, need)) {  // rare: move the reference, rescale what is already stored
-                    const float f = need ? ex2_approx(m2 - bmax) : 1.f;
-                    if (need) m2 = bmax;
-                    row_sum *= f;
-                    for (int bb = b_lo; bb < b; ++bb) {
-                        float t[16];
-                        tmem_ld16_issue(trow + (uint32_t)(16 * bb), t);
-                        tmem_ld_wait(t);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) t[i] *= f;
-                        tmem_st16(trow + (uint32_t)(16 * bb), t);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    med[i] = ex2_approx(med[i] - m2);
-                    if (i < n_ok) row_sum += med[i];
-                }
-                tmem_st16(trow + (uint32_t)(16 * b), med);
-                tmem_ld_wait(ahead);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    prev[i] = cur[i];
-                    cur[i] = next[i];
-                    next[i] = ahead[i];
-                }
+            for (int b = b_lo; b < b_hi; b += 2) {
+                filter_exp_block<W>(trow, b, b_lo, n_blocks, tail, g.half > 0, scale2, ptail, bufa, bufb, st);
+                if (b + 1 < b_hi)
+                    filter_exp_block<W>(trow, b + 1, b_lo, n_blocks, tail, g.half > 0, scale2, ptail, bufb, bufa, st);
             }
             tmem_wait_st();
         }
+        const float m2 = st.m2, row_sum = st.row_sum;
         stamp(tr, seq, kEvEpiA);
         stamp(tr, seq, kEvEpiXMax);
         stamp(tr, seq, kEvEpiB);
@@ -338,32 +394,31 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
         const int rows_here = min(32, g.rows_valid - lw * 32);
         const int c = lane & 15, rsel = lane >> 4;
         const int n_steps = (rows_here - rsel + 1) >> 1;  // rows rsel + 2k < rows_here
-        const int64_t step = 2 * (int64_t)g.F;
-        float *obase = g.out + (int64_t)(lw * 32 + rsel) * g.F + g.f0 + c;
+        // 32-bit element offsets from the tile's first row (at most 128 rows of 1500 frames): one multiply-add and
+        // one widening add per store instead of a 64-bit running pointer
+        const int step = 2 * g.F;
+        float *obase = g.out + ((lw * 32 + rsel) * g.F + g.f0 + c);
+        asm volatile("" : "+l"(obase));  // keep the lane's base pointer in a register pair instead of re-deriving it per store
         const float *tsrc = tile + rsel * kTilePitch + c;
-        float v[16], ahead[16];
+        float v[16];
         tmem_ld16_issue(trow + (uint32_t)(16 * b_lo), v);
         tmem_ld_wait(v);
         for (int b = b_lo; b < b_hi; ++b) {
-            tmem_ld16_issue(trow + (uint32_t)(16 * (b + 1)), ahead);
 #pragma unroll
             for (int i = 0; i < 16; ++i) tile[lane * kTilePitch + i] = v[i] * inv_sum;
+            tmem_ld16_issue(trow + (uint32_t)(16 * (b + 1)), v);  // v is free again: the next block lands behind the stores
             __syncwarp();
             float o[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) o[k] = tsrc[k * 2 * kTilePitch];  // all reads in flight before the stores
             if (g.f0 + 16 * b + c < g.f1) {
-                float *p = obase + 16 * b;
+                const int o0 = 16 * b;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    if (k < n_steps) st_stream(p, o[k]);
-                    p += step;
-                }
+                for (int k = 0; k < 16; ++k)
+                    if (k < n_steps) st_stream(obase + (o0 + k * step), o[k]);
             }
             __syncwarp();
-            tmem_ld_wait(ahead);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = ahead[i];
+            tmem_ld_wait(v);
         }
     }
     stamp(tr, seq, kEvEpiC);
@@ -385,7 +440,8 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
     if (tid == 0) {
         mbar_init(bar(kKFull), 1);
         mbar_init(bar(kQFull), 1);
-        mbar_init(bar(kOpReady), kSplitThreads);
+        mbar_init(bar(kKLoReady), kSplitThreads);
+        mbar_init(bar(kQLoReady), kSplitThreads);
         mbar_init(bar(kKFree), 1);
         mbar_init(bar(kOpFree), 1);
         for (int i = 0; i < 2; ++i) {
@@ -483,23 +539,38 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
             mbar_wait(bar(kAccEmpty + buf), (use & 1u) ^ 1u);  // epilogue drained this accumulator
             if (buf) ++acc_use1; else ++acc_use0;
             stamp(tr, n_tile, kEvMmaAccEmpty);
-            mbar_wait(bar(kOpReady), n_tile & 1u);
-            stamp(tr, n_tile, kEvMmaAReady);
-            tc_fence_after();
             const int n_cols = min(kAccCols, (g.n_mma + 15) & ~15);  // UMMA N: multiple of 16
             const uint32_t idesc = instr_desc_tf32(kRows, n_cols);
             const uint32_t d = tm + buf * kAccCols + (uint32_t)g.mcol0;
-            // the two passes that read K_hi first (lo*hi, hi*hi), so that K_hi can be refilled while hi*lo still runs
+            // Pass order hi*hi, lo*hi, hi*lo.  hi*hi reads the tiles exactly as TMA landed them, so it is issued
+            // as soon as the boxes are there and runs while the splitters still write the lo twins; lo*hi follows
+            // the Q twin, and K_hi -- read by the first two passes only -- is released for the next head's
+            // load before hi*lo (which waits for the K twin) is issued.
+            mbar_wait(bar(kKFull), n_tile & 1u);
+            mbar_wait(bar(kQFull), n_tile & 1u);
+            tc_fence_after();
+            stamp(tr, n_tile, kEvMmaAReady);
 #pragma unroll
             for (int pass = 0; pass < 3; ++pass) {
-                const uint64_t da = pass == 0 ? da_lo : da_hi;
+                const uint64_t da = pass == 1 ? da_lo : da_hi;
                 const uint64_t db = pass == 2 ? db_lo : db_hi;
+                if (pass == 1) {
+                    mbar_wait(bar(kQLoReady), n_tile & 1u);
+                    tc_fence_after();
+                }
+                if (pass == 2) {
+                    // the K twin is complete: the splitters no longer read K_hi either, so the commit below (it
+                    // covers the two passes issued so far) hands K_hi back to the TMA producer
+                    mbar_wait(bar(kKLoReady), n_tile & 1u);
+                    tc_fence_after();
+                    umma_commit_if(bar(kKFree), elected);
+                    stamp(tr, n_tile, kEvMmaB0);
+                }
 #pragma unroll
                 for (int ks = 0; ks < kHeadDim / 8; ++ks)
                     umma_tf32_ss_if(d, da + (uint64_t)(((ks >> 2) * kQHalfBytes + (ks & 3) * 32) >> 4),
                                     db + (uint64_t)(((ks >> 2) * kKHalfBytes + (ks & 3) * 32) >> 4), idesc, (pass | ks) != 0,
                                     elected);
-                if (pass == 1) umma_commit_if(bar(kKFree), elected);
             }
             umma_commit_if(bar(kOpFree), elected);
             umma_commit_if(bar(kAccFull + buf), elected);
@@ -517,15 +588,25 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
             mbar_wait(bar(kOpFree), (n_tile & 1u) ^ 1u);  // the previous tile's MMAs no longer read the lo twins (first lap passes)
             mbar_wait(bar(kKFull), n_tile & 1u);
             stamp(tr, n_tile, kEvSplFull);
+            if (a.dbg & 0x100u) {  // experiment: Q twin first
+                mbar_wait(bar(kQFull), n_tile & 1u);
+                split_lo<kQBytes>(smem + kOffQHi, smem + kOffQLo, t);
+                fence_proxy_async_smem();
+                mbar_arrive(bar(kQLoReady));
+            }
             for (int half = 0; half < 2; ++half)
                 for (int c = 0; c < g.n_chunks; ++c)
                     split_lo<kBoxBytes>(smem + kOffKHi + half * kKHalfBytes + c * kBoxBytes,
                                         smem + kOffKLo + half * kKHalfBytes + c * kBoxBytes, t);
-            stamp(tr, n_tile, kEvSplK0Done);
-            mbar_wait(bar(kQFull), n_tile & 1u);
-            split_lo<kQBytes>(smem + kOffQHi, smem + kOffQLo, t);
             fence_proxy_async_smem();  // generic-proxy stores must be visible to the tensor core's async proxy
-            mbar_arrive(bar(kOpReady));
+            mbar_arrive(bar(kKLoReady));
+            stamp(tr, n_tile, kEvSplK0Done);
+            if (!(a.dbg & 0x100u)) {
+                mbar_wait(bar(kQFull), n_tile & 1u);
+                split_lo<kQBytes>(smem + kOffQHi, smem + kOffQLo, t);
+                fence_proxy_async_smem();
+                mbar_arrive(bar(kQLoReady));
+            }
             stamp(tr, n_tile, kEvSplQDone);
             ++n_tile;
         }
