@@ -3,6 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from whisper_char_alignment_b200 import _cabi
+if os.environ.get("WCA_LIB"):  # A/B timing against another build of the library
+    _cabi.LIB_PATH = os.path.abspath(os.environ["WCA_LIB"])
 
 shape = sys.argv[1] if len(sys.argv) > 1 else "timit"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
@@ -45,7 +47,8 @@ a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tru
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 times = []
 for _ in range(reps):
-    flush.zero_()
+    for _ in range(8):  # ~0.3 ms of queued GPU work: the capture launch (144 tensor-map encodes on the host) is enqueued before
+        flush.zero_()   # the GPU reaches event a, so the events time the kernel and not the host; also flushes L2
     a.record()
     capture()
     b_.record(); torch.cuda.synchronize()

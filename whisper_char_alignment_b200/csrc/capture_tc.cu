@@ -55,7 +55,7 @@ constexpr int kQBytes = 2 * kQHalfBytes;                 // 32768
 constexpr int kMaxChunks = kAccCols / kChunk;            // 4 boxes of 64 frames cover an accumulator
 constexpr int kKHalfBytes = kMaxChunks * kBoxBytes;      // K slab, one column half: 256 frames x 128 B
 constexpr int kKBytes = 2 * kKHalfBytes;                 // 65536
-constexpr int kTilePitch = 17;           // transpose tile pitch (odd: conflict-free column writes)
+constexpr int kTilePitch = 20;           // transpose tile pitch: 16-byte aligned rows, conflict-free 128-bit row writes
 constexpr int kSplitThreads = 128;
 constexpr int kEpiThreads = 128;
 
@@ -289,10 +289,13 @@ __device__ __forceinline__ void filter_exp_block(uint32_t trow, int b, int b_lo,
 }
 
 // The three sweeps of one tile by one epilogue warpgroup (thread <-> token row).
+// Returns true when the accumulator has already been handed back (mbarrier `acc_empty`): that happens as soon as the
+// last block of the store sweep is in registers, one block of stores before the tile is finished.
 template <int W>
-__device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a, unsigned char *smem, uint32_t acc,
+__device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a, unsigned char *smem, uint32_t acc,
                                               int grp, int ewarp, int lane, uint32_t csize, uint32_t x_parity,
-                                              bool tr, uint32_t seq) {
+                                              bool tr, uint32_t seq, uint32_t acc_empty) {
+    bool released = false;
     // Mirrored tiles (Geo::dup): lane quarters 2 and 3 hold a copy of token rows 0..63, so warps
     // 2/3 (other two schedulers) take the second half of the columns of the rows of warps 0/1.
     const int lw = g.dup ? (ewarp & 1) : ewarp;  // logical 32-row group
@@ -394,34 +397,49 @@ __device__ __forceinline__ void epilogue_tile(const Geo &g, const KernelArgs &a,
         const int rows_here = min(32, g.rows_valid - lw * 32);
         const int c = lane & 15, rsel = lane >> 4;
         const int n_steps = (rows_here - rsel + 1) >> 1;  // rows rsel + 2k < rows_here
-        // 32-bit element offsets from the tile's first row (at most 128 rows of 1500 frames): one multiply-add and
+        // 32-bit element offsets from the lane's first row (at most 128 rows of 1500 frames): one multiply-add and
         // one widening add per store instead of a 64-bit running pointer
         const int step = 2 * g.F;
         float *obase = g.out + ((lw * 32 + rsel) * g.F + g.f0 + c);
         asm volatile("" : "+l"(obase));  // keep the lane's base pointer in a register pair instead of re-deriving it per store
         const float *tsrc = tile + rsel * kTilePitch + c;
+        float4 *tdst = reinterpret_cast<float4 *>(tile + lane * kTilePitch);
         float v[16];
         tmem_ld16_issue(trow + (uint32_t)(16 * b_lo), v);
         tmem_ld_wait(v);
         for (int b = b_lo; b < b_hi; ++b) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) tile[lane * kTilePitch + i] = v[i] * inv_sum;
-            tmem_ld16_issue(trow + (uint32_t)(16 * (b + 1)), v);  // v is free again: the next block lands behind the stores
+            for (int i = 0; i < 4; ++i)
+                tdst[i] = make_float4(v[4 * i] * inv_sum, v[4 * i + 1] * inv_sum, v[4 * i + 2] * inv_sum, v[4 * i + 3] * inv_sum);
+            if (b + 1 < b_hi) {
+                tmem_ld16_issue(trow + (uint32_t)(16 * (b + 1)), v);  // v is free again: the next block lands behind the stores
+            } else {
+                // nothing of this tile is left in tensor memory: the MMA issuer may refill the accumulator now
+                tc_fence_before();
+                mbar_arrive(acc_empty);
+                released = true;
+            }
             __syncwarp();
             float o[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) o[k] = tsrc[k * 2 * kTilePitch];  // all reads in flight before the stores
             if (g.f0 + 16 * b + c < g.f1) {
                 const int o0 = 16 * b;
+                if (n_steps == 16) {  // all 32 rows of the warp are token rows: no per-store predicate
 #pragma unroll
-                for (int k = 0; k < 16; ++k)
-                    if (k < n_steps) st_stream(obase + (o0 + k * step), o[k]);
+                    for (int k = 0; k < 16; ++k) st_stream(obase + (o0 + k * step), o[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        if (k < n_steps) st_stream(obase + (o0 + k * step), o[k]);
+                }
             }
             __syncwarp();
             tmem_ld_wait(v);
         }
     }
     stamp(tr, seq, kEvEpiC);
+    return released;
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -627,11 +645,14 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
                 tc_fence_after();
             }
             stamp(tr, seq, kEvEpiAccFull);
-            epilogue_tile<W>(g, a, smem, tmem_base + (uint32_t)grp * kAccCols, grp, ewarp, lane, csize, n_x & 1u, tr, seq);
+            const bool released = epilogue_tile<W>(g, a, smem, tmem_base + (uint32_t)grp * kAccCols, grp, ewarp, lane, csize,
+                                                   n_x & 1u, tr, seq, bar(kAccEmpty + grp));
             ++n_x;
             if (g.n_own > 0) {
-                tc_fence_before();
-                mbar_arrive(bar(kAccEmpty + grp));
+                if (!released) {
+                    tc_fence_before();
+                    mbar_arrive(bar(kAccEmpty + grp));
+                }
                 ++acc_use;
             }
         }
