@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
         if (lane < head) xs[lane] = p.negate ? -ld_stream(xg + lane) : ld_stream(xg + lane);
         const float4 *g4 = reinterpret_cast<const float4 *>(xg + head);
         float4 *s4 = reinterpret_cast<float4 *>(xs + head);
-#pragma unroll 8
-        for (int e = lane; e < body; e += 32) {  // independent loads: 4 KB of requests in flight per warp
+#pragma unroll 16
+        for (int e = lane; e < body; e += 32) {  // independent loads: 8 KB of requests in flight per warp
             float4 v = ld_stream4(g4 + e);
             if (p.negate) v = make_float4(-v.x, -v.y, -v.z, -v.w);
             s4[e] = v;
@@ -114,6 +114,57 @@ __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
         for (int e = head + 4 * body + lane; e < total; e += 32) xs[e] = p.negate ? -ld_stream(xg + e) : ld_stream(xg + e);
         __syncwarp();
     }
+    if constexpr (kStaged && kTraceSmem) {
+        // ---- forward sweep, everything on chip: a branch-free step --------------------------------------------
+        // Lane l handles table rows l*R+1 .. l*R+R at column index c = s - l (0-based).  No cell is ever skipped:
+        // a lane that has not started keeps +inf in its strip (inf + 0 = inf: its x stays 0 until the first
+        // predicated load), a lane past the last column or on rows >= N computes values nobody reads (rows only
+        // feed the rows below them), so only the loads and the trace store are predicated and the step has no
+        // divergent branch, no reconvergence barrier and no index arithmetic beyond one pointer bump.
+        const int row0 = lane * R;
+        float left[R], x[R];
+        const float *xrow[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            left[r] = INFINITY;
+            xrow[r] = xs + min(row0 + r, N - 1) * M - lane;  // xrow[r][s] = x[row][column s - lane]
+            x[r] = lane == 0 ? xrow[r][0] : 0.f;             // column 0 is consumed at step 0 by lane 0 only
+        }
+        float diag_top = (lane == 0) ? 0.f : INFINITY;  // cost[row above strip][c]; cost[0][0] = 0 for lane 0
+        Word *tcol = trace + lane - 32 * lane;          // tcol[32 * s] = trace[(s - lane) * 32 + lane]
+        const int n_steps = M + (N + R - 1) / R - 1;    // the last strip with rows < N finishes column M - 1
+        int c = -lane;
+#pragma unroll 4
+        for (int s = 0; s < n_steps; ++s, ++c) {
+            float up_top = __shfl_up_sync(0xffffffffu, left[R - 1], 1);  // cost[row0][c + 1] of the table, from the strip above
+            if (lane == 0) up_top = INFINITY;
+            const bool act = (unsigned)c < (unsigned)M;
+            const bool act_next = (unsigned)(c + 1) < (unsigned)M;
+            float xc[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                xc[r] = x[r];
+                if (act_next) x[r] = xrow[r][s + 1];  // next column in flight while this one is computed
+            }
+            Word tw = 0;
+            float c0 = diag_top;  // cost[i-1][j-1]
+            float c1 = up_top;    // cost[i-1][j]
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float c2 = left[r];  // cost[i][j-1]
+                const bool d0 = (c0 < c1) & (c0 < c2);
+                const bool d1 = (c1 < c0) & (c1 < c2);
+                const float cm = d0 ? c0 : (d1 ? c1 : c2);
+                tw |= d0 ? (Word)0 : (d1 ? (Word)((Word)1 << (2 * r)) : (Word)((Word)2 << (2 * r)));
+                const float cost = __fadd_rn(xc[r], cm);
+                c0 = c2;    // this row's old value is the next row's diagonal
+                c1 = cost;  // this row's new value is the next row's "up"
+                left[r] = cost;
+            }
+            diag_top = up_top;
+            if (act) tcol[32 * s] = tw;
+        }
+    } else {
     const bool flip = p.negate && !staged;
 
     // ---- forward sweep: lane l handles table rows l*R+1 .. l*R+R, column j = step - l + 1 ------
@@ -204,6 +255,7 @@ __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
             trace[(int64_t)(j - 1) * 32 + lane] = tw;
         }
     }
+    }
     __syncwarp();
 
     // ---- backtrace (sequential by nature), lane 0 ---------------------------------------------
@@ -212,6 +264,24 @@ __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
         int32_t *pt = p.path_text ? p.path_text + u.path_off : nullptr;
         int32_t *pj = p.path_time ? p.path_time + u.path_off : nullptr;
         int bi = N, bj = M, pos = cap;
+        if (!pt) {
+            // Only the jump frames are wanted (the product path): branch-free interior walk, one shared-memory
+            // read per step on the chain; the two borders (column 0 -> text steps, row 0 -> time steps) need no trace.
+            constexpr int kShift = R == 1 ? 0 : (R == 2 ? 1 : (R == 4 ? 2 : (R == 8 ? 3 : (R == 16 ? 4 : 5))));
+            while (bi > 0 && bj > 0) {
+                const int row = bi - 1;
+                const Word w = trace[(bj - 1) * 32 + (row >> kShift)];
+                const uint32_t code = (uint32_t)(w >> (2 * (row & (R - 1)))) & 3u;
+                // first path point of a text row: the step out of it changes the row
+                if (code != 2u) jump_s[row] = bj - 1;
+                bi -= code != 2u;
+                bj -= code != 1u;
+                --pos;
+            }
+            for (; bi > 0; --bi, --pos) jump_s[bi - 1] = -1;  // column 0: text steps only, "frame -1" as upstream's index arithmetic gives
+            pos -= bj;                                          // row 0: time steps only
+            bj = 0;
+        }
         while (bi > 0 || bj > 0) {
             --pos;
             if (pt) {
