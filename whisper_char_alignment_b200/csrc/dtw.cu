@@ -258,30 +258,41 @@ __global__ void __launch_bounds__(128) dtw_align_kernel(const DtwLaunch p) {
     }
     __syncwarp();
 
-    // ---- backtrace (sequential by nature), lane 0 ---------------------------------------------
-    if (lane == 0) {
+    // ---- backtrace -------------------------------------------------------------------------------
+    // Only the jump frames are wanted on the product path, and the walk leaves a text row exactly once: the whole
+    // warp looks at the 32 trace cells to the left of the current one in that row, a ballot finds the nearest cell
+    // whose step changes the row (code 0 / 1), and the walk moves up from there.  One shared-memory read, one
+    // ballot and one shuffle per ROW (plus one per 32 consecutive time steps) instead of one dependent read per
+    // path point.  The borders need no trace: a row reached at column 0 keeps the -1 its jump slot was initialised
+    // with (upstream's index arithmetic gives frame -1 there), row 0 only takes time steps.
+    if (!p.path_text) {
+        constexpr int kShift = R == 1 ? 0 : (R == 2 ? 1 : (R == 4 ? 2 : (R == 8 ? 3 : (R == 16 ? 4 : 5))));
+        int row = N - 1, col = M - 1, n_diag = 0;
+        while (row >= 0 && col >= 0) {
+            const int cc = col - lane;
+            uint32_t code = 2u;
+            if (cc >= 0) {
+                const Word w = trace[cc * 32 + (row >> kShift)];
+                code = (uint32_t)(w >> (2 * (row & (R - 1)))) & 3u;
+            }
+            const uint32_t leaves = __ballot_sync(0xffffffffu, code != 2u);
+            if (leaves == 0u) {  // 32 time steps (or the left border)
+                col -= 32;
+                continue;
+            }
+            const int k = __ffs(leaves) - 1;
+            const uint32_t ck = __shfl_sync(0xffffffffu, code, k);
+            if (lane == 0) jump_s[row] = col - k;  // first path point of the text row
+            n_diag += ck == 0u;
+            col -= k + (ck == 0u);
+            --row;
+        }
+        if (lane == 0 && p.path_len) p.path_len[prob] = N + M - n_diag;  // every diagonal step saves one path point
+    } else if (lane == 0) {
         const int cap = N + M;
         int32_t *pt = p.path_text ? p.path_text + u.path_off : nullptr;
         int32_t *pj = p.path_time ? p.path_time + u.path_off : nullptr;
         int bi = N, bj = M, pos = cap;
-        if (!pt) {
-            // Only the jump frames are wanted (the product path): branch-free interior walk, one shared-memory
-            // read per step on the chain; the two borders (column 0 -> text steps, row 0 -> time steps) need no trace.
-            constexpr int kShift = R == 1 ? 0 : (R == 2 ? 1 : (R == 4 ? 2 : (R == 8 ? 3 : (R == 16 ? 4 : 5))));
-            while (bi > 0 && bj > 0) {
-                const int row = bi - 1;
-                const Word w = trace[(bj - 1) * 32 + (row >> kShift)];
-                const uint32_t code = (uint32_t)(w >> (2 * (row & (R - 1)))) & 3u;
-                // first path point of a text row: the step out of it changes the row
-                if (code != 2u) jump_s[row] = bj - 1;
-                bi -= code != 2u;
-                bj -= code != 1u;
-                --pos;
-            }
-            for (; bi > 0; --bi, --pos) jump_s[bi - 1] = -1;  // column 0: text steps only, "frame -1" as upstream's index arithmetic gives
-            pos -= bj;                                          // row 0: time steps only
-            bj = 0;
-        }
         while (bi > 0 || bj > 0) {
             --pos;
             if (pt) {
@@ -436,6 +447,34 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_multi_kernel(const DtwLaun
     }
     __syncthreads();
 
+    if (!p.path_text) {
+        // jump frames only: warp 0 walks row by row with a ballot over 32 trace cells (see dtw_align_kernel)
+        if (warp == 0) {
+            constexpr int kShift = R == 2 ? 1 : 2;
+            static_assert(R == 2 || R == 4, "strip height of the multi-warp kernel");
+            int row = N - 1, col = M - 1, n_diag = 0;
+            while (row >= 0 && col >= 0) {
+                const int cc = col - lane;
+                uint32_t code = 2u;
+                if (cc >= 0) {
+                    const Word w = trace[(int64_t)cc * L + (row >> kShift)];
+                    code = (uint32_t)(w >> (2 * (row & (R - 1)))) & 3u;
+                }
+                const uint32_t leaves = __ballot_sync(0xffffffffu, code != 2u);
+                if (leaves == 0u) {
+                    col -= 32;
+                    continue;
+                }
+                const int k = __ffs(leaves) - 1;
+                const uint32_t ck = __shfl_sync(0xffffffffu, code, k);
+                if (lane == 0) jump_s[row] = col - k;
+                n_diag += ck == 0u;
+                col -= k + (ck == 0u);
+                --row;
+            }
+            if (lane == 0 && p.path_len) p.path_len[prob] = N + M - n_diag;
+        }
+    } else
     if (g == 0) {
         const int cap = N + M;
         int32_t *pt = p.path_text ? p.path_text + u.path_off : nullptr;
