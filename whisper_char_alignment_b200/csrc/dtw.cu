@@ -377,20 +377,19 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_multi_kernel(const DtwLaun
     for (int r = 0; r < R; ++r) left[r] = INFINITY;
     float diag_top = (g == 0) ? 0.f : INFINITY;
     const float *xg = p.matrix + u.matrix_off;
-    auto load_col = [&](int j, float (&dst)[R]) {  // x[row][j-1] for the strip, 0 outside
+    // Branch-free step (see dtw_align_kernel): rows past N read the last row (their cells feed nobody), columns
+    // outside [0, M) are never loaded (the lookahead registers start at 0, which keeps a strip that has not started
+    // at +inf), and only the loads, the trace store and the hand-over store are predicated.
+    const float *xrow[R];  // xrow[r][s] = x[row][column s - lane] at local step s
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int row = row0 + r;
-            float v = 0.f;
-            if (row < N && j >= 1 && j <= M) v = xg[(int64_t)row * M + (j - 1)];  // L1-cached: 8 steps share a sector
-            dst[r] = v;  // the sign is applied where the value is consumed: touching it here would wait for the load
-        }
-    };
+    for (int r = 0; r < R; ++r) xrow[r] = xg + (int64_t)min(row0 + r, N - 1) * M - lane;
     // kAhead columns of lookahead in registers (ncu: 40 % of the stall samples were long-scoreboard waits on the
     // cost loads); the step loop is unrolled by kAhead so that the ring index is a compile-time constant.
     float xq[kAhead][R];
 #pragma unroll
-    for (int d = 0; d < kAhead; ++d) load_col(d + 1 - lane, xq[d]);
+    for (int d = 0; d < kAhead; ++d)
+#pragma unroll
+        for (int r = 0; r < R; ++r) xq[d][r] = (unsigned)(d - lane) < (unsigned)M ? xrow[r][d] : 0.f;
     const int n_steps = M + 31;  // local steps of this warp; column of a lane: j = s - lane + 1
     const volatile unsigned long long *edge_in = edge + (size_t)(warp > 0 ? warp - 1 : 0) * edge_stride;
     volatile unsigned long long *edge_out = edge + (size_t)(warp < WPP - 1 ? warp : 0) * edge_stride;
@@ -410,38 +409,41 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_multi_kernel(const DtwLaun
 #pragma unroll
       for (int d = 0; d < kAhead; ++d) {
         const int s = s0 + d;
-        const int j = s - lane + 1;
+        const int c = s - lane;  // 0-based column of this lane at this step
+        const bool act = (unsigned)c < (unsigned)M;
         float up_top = __shfl_up_sync(0xffffffffu, left[R - 1], 1);
         if (lane == 0) {
             up_top = INFINITY;  // cost[0][j], j >= 1 (first warp)
-            if (warp > 0 && j <= M) up_top = __uint_as_float((uint32_t)edge_in[j - 1]);  // published: checked above
+            if (warp > 0 && act) up_top = __uint_as_float((uint32_t)edge_in[c]);  // published: checked above
         }
         float xc[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) xc[r] = flip ? -xq[d][r] : xq[d][r];
-        load_col(j + kAhead, xq[d]);
-        if (j >= 1 && j <= M) {
-            Word tw = 0;
-            float c0 = diag_top;
-            float c1 = up_top;
+        if ((unsigned)(c + kAhead) < (unsigned)M) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float c2 = left[r];
-                // selects, not branches: the lanes of a warp take different cases in every cell
-                const bool d0 = (c0 < c1) & (c0 < c2);
-                const bool d1 = (c1 < c0) & (c1 < c2);
-                const float c = d0 ? c0 : (d1 ? c1 : c2);
-                const uint32_t code = d0 ? 0u : (d1 ? 1u : 2u);
-                const float cost = __fadd_rn(xc[r], c);
-                tw |= (Word)((Word)code << (2 * (r % (4 * (int)sizeof(Word)))));
-                c0 = c2;
-                c1 = cost;
-                left[r] = cost;
-            }
-            diag_top = up_top;
-            trace[(int64_t)(j - 1) * L + g] = tw;
+            for (int r = 0; r < R; ++r) xq[d][r] = xrow[r][s + kAhead];  // L1-cached: 8 steps share a sector
+        }
+        Word tw = 0;
+        float c0 = diag_top;
+        float c1 = up_top;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float c2 = left[r];
+            // selects, not branches: the lanes of a warp take different cases in every cell
+            const bool d0 = (c0 < c1) & (c0 < c2);
+            const bool d1 = (c1 < c0) & (c1 < c2);
+            const float cm = d0 ? c0 : (d1 ? c1 : c2);
+            tw |= d0 ? (Word)0 : (d1 ? (Word)((Word)1 << (2 * r)) : (Word)((Word)2 << (2 * r)));
+            const float cost = __fadd_rn(xc[r], cm);
+            c0 = c2;
+            c1 = cost;
+            left[r] = cost;
+        }
+        diag_top = up_top;
+        if (act) {
+            trace[c * L + g] = tw;
             if (lane == 31 && warp < WPP - 1)
-                edge_out[j - 1] = ((unsigned long long)(uint32_t)j << 32) | __float_as_uint(left[R - 1]);
+                edge_out[c] = ((unsigned long long)(uint32_t)(c + 1) << 32) | __float_as_uint(left[R - 1]);
         }
       }
     }
