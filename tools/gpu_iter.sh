@@ -1,10 +1,14 @@
 #!/bin/bash
-# One development iteration on a B200: GPU suite, capture timing (against the previous build when tools/libwca_prev.so exists), role timeline.
+# One development iteration on a B200: GPU suite, capture timing (against other builds of the library under tools/), role timeline.
 mkdir -p gpurun_out
+if [ "$1" != "notest" ]; then
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/t_iter.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/t_iter.log
-python tools/ncu_capture.py timit 16
-[ -f tools/libwca_prev.so ] && WCA_LIB=tools/libwca_prev.so python tools/ncu_capture.py timit 16
-python tools/ncu_capture.py timit 32
-python tools/ncu_capture.py libri 8
-[ -f tools/libwca_prev.so ] && WCA_LIB=tools/libwca_prev.so python tools/ncu_capture.py libri 8
+fi
+for lib in "" tools/libwca_head.so tools/libwca_prev.so; do
+  [ -n "$lib" ] && [ ! -f "$lib" ] && continue
+  echo "== lib: ${lib:-current}"
+  WCA_LIB=$lib python tools/ncu_capture.py timit 16
+  WCA_LIB=$lib python tools/ncu_capture.py timit 32
+  WCA_LIB=$lib python tools/ncu_capture.py libri 8
+done
 python tools/trace_capture.py timit 16 3 2>&1 | tail -17

@@ -55,7 +55,7 @@ constexpr int kQBytes = 2 * kQHalfBytes;                 // 32768
 constexpr int kMaxChunks = kAccCols / kChunk;            // 4 boxes of 64 frames cover an accumulator
 constexpr int kKHalfBytes = kMaxChunks * kBoxBytes;      // K slab, one column half: 256 frames x 128 B
 constexpr int kKBytes = 2 * kKHalfBytes;                 // 65536
-constexpr int kTilePitch = 20;           // transpose tile pitch: 16-byte aligned rows, conflict-free 128-bit row writes
+constexpr int kTilePitch = 16;           // transpose tile pitch: no padding, 16-byte chunks XOR-swizzled by (row / 2) & 3
 constexpr int kSplitThreads = 128;
 constexpr int kEpiThreads = 128;
 
@@ -176,6 +176,23 @@ __device__ __forceinline__ void split_lo(const unsigned char *hi, unsigned char 
 #pragma unroll
     for (int it = 0; it < kIters; ++it)
         dst[it * kSplitThreads + t] = make_float4(tf32_lo(v[it].x), tf32_lo(v[it].y), tf32_lo(v[it].z), tf32_lo(v[it].w));
+}
+
+// Mirrored Q tile (Geo::dup): rows 64..127 of each column half are a second copy of rows 0..63, so one box is read
+// and its lo twin is written to both (half the shared-memory reads of a plain split).
+__device__ __forceinline__ void split_lo_dup(const unsigned char *hi, unsigned char *lo, int t) {
+    constexpr int kIters = kBoxBytes / 16 / kSplitThreads;
+    const float4 *src = reinterpret_cast<const float4 *>(hi);
+    float4 *dst = reinterpret_cast<float4 *>(lo);
+    float4 v[kIters];
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) v[it] = src[it * kSplitThreads + t];
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+        const float4 l = make_float4(tf32_lo(v[it].x), tf32_lo(v[it].y), tf32_lo(v[it].z), tf32_lo(v[it].w));
+        dst[it * kSplitThreads + t] = l;
+        dst[kBoxBytes / 16 + it * kSplitThreads + t] = l;
+    }
 }
 
 // Sliding median over a 16-column block; every index is a compile time constant after unrolling, so the
@@ -402,15 +419,21 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
         const int step = 2 * g.F;
         float *obase = g.out + ((lw * 32 + rsel) * g.F + g.f0 + c);
         asm volatile("" : "+l"(obase));  // keep the lane's base pointer in a register pair instead of re-deriving it per store
-        const float *tsrc = tile + rsel * kTilePitch + c;
+        // 32 x 16 tile without padding; the 16-byte chunk j of row r sits in slot j ^ ((r >> 1) & 3).  Row writes
+        // (128-bit, 8 lanes per wavefront: rows r, r+2, r+4, r+6 share 16 banks) and column reads (lanes = 16 columns
+        // x 2 rows; both rows of an instruction have the same (r >> 1) & 3 = k & 3) are then both conflict-free.
+        const int sw = (lane >> 1) & 3;
         float4 *tdst = reinterpret_cast<float4 *>(tile + lane * kTilePitch);
+        const float *tsrc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tsrc[j] = tile + rsel * kTilePitch + 4 * ((c >> 2) ^ j) + (c & 3);
         float v[16];
         tmem_ld16_issue(trow + (uint32_t)(16 * b_lo), v);
         tmem_ld_wait(v);
         for (int b = b_lo; b < b_hi; ++b) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                tdst[i] = make_float4(v[4 * i] * inv_sum, v[4 * i + 1] * inv_sum, v[4 * i + 2] * inv_sum, v[4 * i + 3] * inv_sum);
+                tdst[i ^ sw] = make_float4(v[4 * i] * inv_sum, v[4 * i + 1] * inv_sum, v[4 * i + 2] * inv_sum, v[4 * i + 3] * inv_sum);
             if (b + 1 < b_hi) {
                 tmem_ld16_issue(trow + (uint32_t)(16 * (b + 1)), v);  // v is free again: the next block lands behind the stores
             } else {
@@ -422,7 +445,7 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
             __syncwarp();
             float o[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) o[k] = tsrc[k * 2 * kTilePitch];  // all reads in flight before the stores
+            for (int k = 0; k < 16; ++k) o[k] = tsrc[k & 3][k * 2 * kTilePitch];  // all reads in flight before the stores
             if (g.f0 + 16 * b + c < g.f1) {
                 const int o0 = 16 * b;
                 if (n_steps == 16) {  // all 32 rows of the warp are token rows: no per-store predicate
@@ -608,7 +631,12 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
             stamp(tr, n_tile, kEvSplFull);
             if (a.dbg & 0x100u) {  // experiment: Q twin first
                 mbar_wait(bar(kQFull), n_tile & 1u);
-                split_lo<kQBytes>(smem + kOffQHi, smem + kOffQLo, t);
+                if (g.dup) {
+                    for (int half = 0; half < 2; ++half)
+                        split_lo_dup(smem + kOffQHi + half * kQHalfBytes, smem + kOffQLo + half * kQHalfBytes, t);
+                } else {
+                    split_lo<kQBytes>(smem + kOffQHi, smem + kOffQLo, t);
+                }
                 fence_proxy_async_smem();
                 mbar_arrive(bar(kQLoReady));
             }
@@ -621,7 +649,12 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
             stamp(tr, n_tile, kEvSplK0Done);
             if (!(a.dbg & 0x100u)) {
                 mbar_wait(bar(kQFull), n_tile & 1u);
-                split_lo<kQBytes>(smem + kOffQHi, smem + kOffQLo, t);
+                if (g.dup) {
+                    for (int half = 0; half < 2; ++half)
+                        split_lo_dup(smem + kOffQHi + half * kQHalfBytes, smem + kOffQLo + half * kQHalfBytes, t);
+                } else {
+                    split_lo<kQBytes>(smem + kOffQHi, smem + kOffQLo, t);
+                }
                 fence_proxy_async_smem();
                 mbar_arrive(bar(kQLoReady));
             }
