@@ -11,4 +11,4 @@ for lib in "" tools/libwca_head.so tools/libwca_prev.so; do
   WCA_LIB=$lib python tools/ncu_capture.py timit 32
   WCA_LIB=$lib python tools/ncu_capture.py libri 8
 done
-python tools/trace_capture.py timit 16 3 2>&1 | tail -17
+python tools/trace_capture.py ${2:-timit} ${3:-16} 3 2>&1 | tail -17

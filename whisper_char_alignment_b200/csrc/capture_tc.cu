@@ -375,32 +375,37 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
         stamp(tr, seq, kEvEpiB);
         // (m, sum) of the other column half (mirrored tiles) and of the other cluster ranks; the statistics
         // buffers alternate with the tile parity so that nobody overwrites a pair a slower peer still reads
-        float *smax = sstat + (x_parity * 2 + 0) * kRows;
-        float *ssum = sstat + (x_parity * 2 + 1) * kRows;
+        float2 *spair = reinterpret_cast<float2 *>(sstat + x_parity * 2 * kRows);  // {m, sum} per slot
         float gmax = m2, gsum = row_sum;
         if (g.dup) {
-            smax[ewarp * 32 + lane] = m2;
-            ssum[ewarp * 32 + lane] = row_sum;
+            spair[ewarp * 32 + lane] = make_float2(m2, row_sum);
             named_bar_sync(1 + grp, kEpiThreads);
-            const float pm = smax[(ewarp ^ 2) * 32 + lane], ps = ssum[(ewarp ^ 2) * 32 + lane];
-            gmax = fmaxf(m2, pm);
-            gsum = (m2 > -INFINITY ? row_sum * ex2_approx(m2 - gmax) : 0.f) + (pm > -INFINITY ? ps * ex2_approx(pm - gmax) : 0.f);
+            const float2 o = spair[(ewarp ^ 2) * 32 + lane];
+            gmax = fmaxf(m2, o.x);
+            gsum = (m2 > -INFINITY ? row_sum * ex2_approx(m2 - gmax) : 0.f) + (o.x > -INFINITY ? o.y * ex2_approx(o.x - gmax) : 0.f);
         }
         if (csize > 1) {
             // every CTA of the cluster takes part, even with no own frames
-            smax[row] = row_ok ? m2 : -INFINITY;
-            ssum[row] = row_ok ? row_sum : 0.f;
+            spair[row] = row_ok ? make_float2(m2, row_sum) : make_float2(-INFINITY, 0.f);
             named_bar_sync(1 + grp, kEpiThreads);
-            if (row == 0)
-                for (uint32_t r = 0; r < csize; ++r) mbar_arrive_remote(bar_xmax, r);
+            // lane r of the first warp signals rank r: ONE instruction with csize active lanes.  A loop of release-arrives
+            // in one thread paid the cluster-scope release (~1.2 k cycles) once per rank, 9-10 k cycles per head.
+            if ((uint32_t)row < csize) mbar_arrive_remote(bar_xmax, (uint32_t)row);
             mbar_wait_cluster(bar_xmax, x_parity);
+            // all ranks' pairs in flight at once: a dependent chain of remote loads (maximum first, then a conditional
+            // load of each sum) cost ~16 distributed-shared-memory round trips per head, 10.8 k of a 22.7 k-cycle epilogue
+            float2 pr[8];
+#pragma unroll
+            for (uint32_t r = 0; r < 8; ++r)
+                if (r < csize) pr[r] = ld_dsmem_f32x2(&spair[row], r);
             gmax = -INFINITY;
-            for (uint32_t r = 0; r < csize; ++r) gmax = fmaxf(gmax, ld_dsmem_f32(&smax[row], r));
+#pragma unroll
+            for (uint32_t r = 0; r < 8; ++r)
+                if (r < csize) gmax = fmaxf(gmax, pr[r].x);
             gsum = 0.f;
-            for (uint32_t r = 0; r < csize; ++r) {
-                const float mr = ld_dsmem_f32(&smax[row], r);
-                if (mr > -INFINITY) gsum += ld_dsmem_f32(&ssum[row], r) * ex2_approx(mr - gmax);
-            }
+#pragma unroll
+            for (uint32_t r = 0; r < 8; ++r)
+                if (r < csize && pr[r].x > -INFINITY) gsum += pr[r].y * ex2_approx(pr[r].x - gmax);
         }
         inv_sum = (m2 > -INFINITY ? ex2_approx(m2 - gmax) : 0.f) / gsum;  // this thread's e values are relative to its own m
         stamp(tr, seq, kEvEpiXSum);
@@ -506,7 +511,7 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
     if (warp == 0) {
         // ================= TMA producer: boxes land directly in the operand buffers =================
         uint32_t n_tile = 0;
-        const bool tr = a.trace && blockIdx.x == 0 && lane == 0;
+        const bool tr = a.trace && blockIdx.x == (a.dbg >> 8) && lane == 0;
         const uint32_t q_hi = smem_u32(smem + kOffQHi), k_hi = smem_u32(smem + kOffKHi);
         for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
             const Geo g = decode_tile<W>(a, tile, crank, csize);
@@ -561,7 +566,7 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
         // ================= MMA issuer: the whole warp runs the loop, one elected lane issues =================
         // (only the tcgen05.mma itself is predicated: descriptor arithmetic stays on the uniform datapath)
         uint32_t n_tile = 0, acc_use0 = 0, acc_use1 = 0, it = 0;
-        const bool tr = a.trace && blockIdx.x == 0 && lane == 0;
+        const bool tr = a.trace && blockIdx.x == (a.dbg >> 8) && lane == 0;
         const uint32_t elected = elect_one() ? 1u : 0u;
         const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
         // K-major, 128-byte swizzle: 8-row groups are 1024 B apart; 8 tf32 = 32 B along the row, the second
@@ -622,7 +627,7 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
         // ================= operand splitters: write the lo twins =================
         const int t = tid - 4 * 32;
         uint32_t n_tile = 0;
-        const bool tr = a.trace && blockIdx.x == 0 && t == 0;
+        const bool tr = a.trace && blockIdx.x == (a.dbg >> 8) && t == 0;
         for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
             const Geo g = decode_tile<W>(a, tile, crank, csize);
             if (!g.live || g.n_own == 0) continue;
@@ -665,7 +670,7 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
         // ================= epilogue warpgroups (A: even tiles, B: odd tiles) =================
         const int grp = (warp - 8) >> 2, ewarp = warp & 3;
         uint32_t it = 0, acc_use = 0, n_x = 0;
-        const bool tr = a.trace && blockIdx.x == 0 && ewarp == 0 && lane == 0;
+        const bool tr = a.trace && blockIdx.x == (a.dbg >> 8) && ewarp == 0 && lane == 0;
         for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
             const Geo g = decode_tile<W>(a, tile, crank, csize);
             if (!g.live) continue;

@@ -37,6 +37,15 @@ __device__ __forceinline__ float ld_dsmem_f32(const float *local, uint32_t rank)
     return v;
 }
 
+// {m, sum} pair of one row from a peer CTA.  Volatile (stays behind the caller's mbarrier wait) but without a memory
+// clobber and without data dependences between ranks: the loads of all ranks are in flight together, one
+// distributed-shared-memory round trip instead of one per rank.
+__device__ __forceinline__ float2 ld_dsmem_f32x2(const float2 *local, uint32_t rank) {
+    float2 v;
+    asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(map_to_rank(smem_u32(local), rank)));
+    return v;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
