@@ -137,7 +137,8 @@ WCA_API int wca_medfilt_softmax(const float *d_in, int64_t n_rows, int64_t ld_in
  *   score[head] = w_col * sum_f ||a[:,f]||_2 + w_row * sum_t ||a[t,:]||_2
  *                 - w_cov * (sum_f max(sum_t a[t,f], 0.5) - 0.5 F)
  * Terms with a weight <= 0 are skipped exactly as the reference does.  Output
- * d_scores + score_off, n_heads floats per utterance. */
+ * d_scores + score_off, n_heads floats per utterance.  Any n_frames; more than 1024 token
+ * rows are only accepted with max_frames <= 256 (Whisper caps n_tokens at 448). */
 WCA_API int wca_head_scores(const float *d_ws, const wca_utt_t *d_utts, int n_utts, int n_heads, int max_tokens,
                     int max_frames, float w_colnorm, float w_rownorm, float w_coverage, float *d_scores,
                     wca_stream_t stream);

@@ -193,9 +193,12 @@ int wca_medfilt_softmax(const float *d_in, int64_t n_rows, int64_t ld_in, int n_
 int wca_head_scores(const float *d_ws, const wca_utt_t *d_utts, int n_utts, int n_heads, int max_tokens,
                     int max_frames, float w_colnorm, float w_rownorm, float w_coverage, float *d_scores,
                     wca_stream_t stream) {
-    (void)max_tokens;
     WCA_CHECK_ARG(d_ws && d_utts && d_scores, "wca_head_scores: null pointer");
     WCA_CHECK_ARG(max_frames >= 1, "wca_head_scores: max_frames=%d", max_frames);
+    // rows longer than one 256-column chunk keep their partial norms in a 1024-entry shared buffer
+    WCA_CHECK_ARG(max_frames <= 256 || max_tokens <= 1024,
+                  "wca_head_scores: max_tokens=%d with max_frames=%d (more than 1024 token rows need max_frames <= 256)",
+                  max_tokens, max_frames);
     WCA_CHECK_ARG(n_heads >= 1 && n_heads <= 65535 * 32 && n_utts >= 0 && n_utts <= 65535,
                   "wca_head_scores: bad geometry (%d heads, %d utts)", n_heads, n_utts);
     if (n_utts == 0) return WCA_OK;

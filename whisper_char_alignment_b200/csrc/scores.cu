@@ -20,76 +20,99 @@ __device__ __forceinline__ float block_sum_256(float v, float *scratch /* >= 8 f
     return total;
 }
 
-// grid (n_heads, n_utts), block 256 = 8 warps.  ONE pass over the (T, F) tile: warp w streams rows
-// w, w+8, ... with 128-byte coalesced loads; lane l keeps the partial column statistics of columns
-// l, l+32, ... in registers (kCols of them), so a row contributes to its own norm (warp shuffle tree)
-// and to the column sums at the same time.  The 8 warps' column partials are then combined in a fixed
-// order through shared memory (deterministic).  kCols = ceil(F / 32) rounded up to 8 / 16 / 32 / 48.
-template <int kCols>
+// grid (n_heads, n_utts), block 256 = 8 warps.  ONE pass over the (T, F) tile in chunks of 256 columns: warp w
+// streams rows w, w+8, ... (two per iteration) with 128-byte coalesced loads; lane l keeps the partial column
+// statistics of columns l, l+32, ... of the chunk in registers (8 of them), so a row contributes to its own norm
+// (warp shuffle tree) and to the column sums at the same time.  The 8 warps' column partials are combined in a fixed
+// order through shared memory at the end of every chunk (deterministic).  Rows longer than one chunk (F > 256:
+// LibriSpeech-shaped utterances) accumulate their sum of squares per row in shared memory across chunks - a row always
+// belongs to the same warp - so the register footprint does not grow with F (the earlier 16/32/48-column
+// instantiations ran one CTA per SM at F > 1024 and reached 1.2 TB/s).
+constexpr int kScoreCols = 8;                      // columns per lane and chunk
+constexpr int kScoreChunk = kScoreCols * kWarp;    // 256 columns
+constexpr int kScoreMaxRows = 1024;                // rows whose partial norms fit the shared buffer (Whisper caps T at 448)
 __global__ void __launch_bounds__(256) head_scores_kernel(const float *__restrict__ ws,
                                                           const wca_utt_t *__restrict__ utts, float w_col,
                                                           float w_row, float w_cov, float *__restrict__ scores) {
-    extern __shared__ float col_part[];  // [2][8 warps][kCols * 32]: sum of squares, plain sum
+    constexpr int kCols = kScoreCols;
+    __shared__ float col_part[2 * 8 * kScoreChunk];  // [2][8 warps][256]: sum of squares, plain sum
+    __shared__ float row_ss[kScoreMaxRows];
     __shared__ float scratch[8];
     const wca_utt_t u = utts[blockIdx.y];
     const int T = u.n_tokens, F = u.n_frames;
-    if (F > kCols * kWarp) return;  // served by a wider instantiation (grid y mixes utterance lengths)
-    if (kCols > 8 && F <= (kCols == 16 ? 8 : kCols == 32 ? 16 : 32) * kWarp) return;
     const float *a = ws + u.ws_off + (int64_t)blockIdx.x * T * F;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
     const bool need_cols = w_col > 0.f || w_cov > 0.f;
-
-    float css[kCols], cs[kCols];
-#pragma unroll
-    for (int k = 0; k < kCols; ++k) css[k] = cs[k] = 0.f;
-    float row_part = 0.f;  // sum_t ||a[t,:]||_2        (timing.py:24)
-    // two rows per iteration when the register budget allows: twice the loads in flight per lane
-    constexpr int kRowsPerIter = kCols <= 16 ? 2 : 1;
-    for (int t0 = warp; t0 < T; t0 += warps * kRowsPerIter) {
-        float p[kRowsPerIter][kCols];
-#pragma unroll
-        for (int i = 0; i < kRowsPerIter; ++i) {
-            const int t = t0 + i * warps;
-            const float *r = a + (int64_t)t * F;
-#pragma unroll
-            for (int k = 0; k < kCols; ++k) {
-                const int f = lane + k * kWarp;
-                p[i][k] = (t < T && f < F) ? ld_stream(r + f) : 0.f;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < kRowsPerIter; ++i) {
-            float ss = 0.f;
-#pragma unroll
-            for (int k = 0; k < kCols; ++k) {
-                ss = fmaf(p[i][k], p[i][k], ss);
-                css[k] = fmaf(p[i][k], p[i][k], css[k]);
-                cs[k] += p[i][k];
-            }
-            ss = warp_sum(ss);
-            if (lane == 0 && t0 + i * warps < T) row_part += sqrtf(ss);
-        }
+    const int n_chunks = (F + kScoreChunk - 1) / kScoreChunk;
+    if (n_chunks > 1) {
+        if (T > kScoreMaxRows) __trap();  // surfaces as a launch failure: never a silently wrong score
+        for (int t = threadIdx.x; t < T; t += blockDim.x) row_ss[t] = 0.f;
+        __syncthreads();
     }
+
+    float row_part = 0.f;      // sum_t ||a[t,:]||_2        (timing.py:24)
     float col_part_sum = 0.f;  // sum_f ||a[:,f]||_2        (timing.py:21)
     float cov_part = 0.f;      // sum_f max(sum_t a[t,f], .5) (metrics.py:104-109)
-    if (need_cols) {
-        float *pss = col_part, *ps = col_part + 8 * kCols * kWarp;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int fbase = ch * kScoreChunk;
+        float css[kCols], cs[kCols];
 #pragma unroll
-        for (int k = 0; k < kCols; ++k) {
-            pss[(warp * kCols + k) * kWarp + lane] = css[k];
-            ps[(warp * kCols + k) * kWarp + lane] = cs[k];
-        }
-        __syncthreads();
-        for (int f = threadIdx.x; f < F; f += blockDim.x) {
-            const int k = f >> 5, l = f & 31;
-            float ss = 0.f, s1 = 0.f;
-            for (int w = 0; w < warps; ++w) {  // fixed order
-                ss += pss[(w * kCols + k) * kWarp + l];
-                s1 += ps[(w * kCols + k) * kWarp + l];
+        for (int k = 0; k < kCols; ++k) css[k] = cs[k] = 0.f;
+        constexpr int kRowsPerIter = 2;  // twice the loads in flight per lane
+        for (int t0 = warp; t0 < T; t0 += warps * kRowsPerIter) {
+            float p[kRowsPerIter][kCols];
+#pragma unroll
+            for (int i = 0; i < kRowsPerIter; ++i) {
+                const int t = t0 + i * warps;
+                const float *r = a + (int64_t)t * F + fbase;
+#pragma unroll
+                for (int k = 0; k < kCols; ++k) {
+                    const int f = lane + k * kWarp;
+                    p[i][k] = (t < T && fbase + f < F) ? ld_stream(r + f) : 0.f;
+                }
             }
-            col_part_sum += sqrtf(ss);
-            cov_part += fmaxf(s1, 0.5f);
+#pragma unroll
+            for (int i = 0; i < kRowsPerIter; ++i) {
+                float ss = 0.f;
+#pragma unroll
+                for (int k = 0; k < kCols; ++k) {
+                    ss = fmaf(p[i][k], p[i][k], ss);
+                    css[k] = fmaf(p[i][k], p[i][k], css[k]);
+                    cs[k] += p[i][k];
+                }
+                ss = warp_sum(ss);
+                const int t = t0 + i * warps;
+                if (lane == 0 && t < T) {
+                    if (n_chunks == 1) row_part += sqrtf(ss);
+                    else row_ss[t] += ss;  // rows t = warp (mod 8) are this warp's: no other writer
+                }
+            }
         }
+        if (need_cols) {
+            float *pss = col_part, *ps = col_part + 8 * kScoreChunk;
+#pragma unroll
+            for (int k = 0; k < kCols; ++k) {
+                pss[(warp * kCols + k) * kWarp + lane] = css[k];
+                ps[(warp * kCols + k) * kWarp + lane] = cs[k];
+            }
+            __syncthreads();
+            const int f = threadIdx.x;  // one column of the chunk per thread
+            if (fbase + f < F) {
+                const int k = f >> 5, l = f & 31;
+                float ss = 0.f, s1 = 0.f;
+                for (int w = 0; w < warps; ++w) {  // fixed order
+                    ss += pss[(w * kCols + k) * kWarp + l];
+                    s1 += ps[(w * kCols + k) * kWarp + l];
+                }
+                col_part_sum += sqrtf(ss);
+                cov_part += fmaxf(s1, 0.5f);
+            }
+            if (ch + 1 < n_chunks) __syncthreads();  // the partials are overwritten by the next chunk
+        }
+    }
+    if (n_chunks > 1) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < T; t += blockDim.x) row_part += sqrtf(row_ss[t]);
     }
     const float row_sum = block_sum_256(row_part, scratch);
     const float col_sum = block_sum_256(col_part_sum, scratch);
@@ -172,33 +195,12 @@ __global__ void __launch_bounds__(256) aggregate_heads_kernel(const float *__res
             matrix[u.matrix_off + (int64_t)(t - u.row_begin) * F + f] = acc_s[t * kWarp + lane] / count;
 }
 
-template <int kCols>
-static int launch_head_scores_cols(const float *d_ws, const wca_utt_t *d_utts, int n_utts, int n_heads, float w_col, float w_row,
-                                   float w_cov, float *d_scores, cudaStream_t stream) {
-    const size_t smem = 2u * 8u * kCols * kWarp * sizeof(float);
-    if (smem > 48u * 1024u)
-        WCA_CUDA(cudaFuncSetAttribute(head_scores_kernel<kCols>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_scores_kernel<kCols><<<dim3(n_heads, n_utts), 256, smem, stream>>>(d_ws, d_utts, w_col, w_row, w_cov, d_scores);
-    WCA_LAUNCH_CHECK("head_scores_kernel");
-    return WCA_OK;
-}
-
-// One launch per column-count class that can occur for max_frames (a CTA whose utterance belongs to another
-// class returns immediately), so short utterances do not pay for 48 columns of registers per lane.
 int launch_head_scores(const float *d_ws, const wca_utt_t *d_utts, int n_utts, int n_heads, int max_frames, float w_col,
                        float w_row, float w_cov, float *d_scores, cudaStream_t stream) {
-    if (max_frames > 48 * kWarp) {
-        set_error("wca_head_scores: max_frames=%d exceeds %d", max_frames, 48 * kWarp);
-        return WCA_ERR_UNSUPPORTED;
-    }
-    int rc = launch_head_scores_cols<8>(d_ws, d_utts, n_utts, n_heads, w_col, w_row, w_cov, d_scores, stream);
-    if (rc == WCA_OK && max_frames > 8 * kWarp)
-        rc = launch_head_scores_cols<16>(d_ws, d_utts, n_utts, n_heads, w_col, w_row, w_cov, d_scores, stream);
-    if (rc == WCA_OK && max_frames > 16 * kWarp)
-        rc = launch_head_scores_cols<32>(d_ws, d_utts, n_utts, n_heads, w_col, w_row, w_cov, d_scores, stream);
-    if (rc == WCA_OK && max_frames > 32 * kWarp)
-        rc = launch_head_scores_cols<48>(d_ws, d_utts, n_utts, n_heads, w_col, w_row, w_cov, d_scores, stream);
-    return rc;
+    (void)max_frames;  // any row length: the kernel walks it in chunks of 256 columns
+    head_scores_kernel<<<dim3(n_heads, n_utts), 256, 0, stream>>>(d_ws, d_utts, w_col, w_row, w_cov, d_scores);
+    WCA_LAUNCH_CHECK("head_scores_kernel");
+    return WCA_OK;
 }
 
 int launch_topk_heads(const float *d_scores, const wca_utt_t *d_utts, int n_utts, int n_heads, int32_t *d_sel,
