@@ -66,6 +66,50 @@ def test_dtw_bit_exact_vs_oracle_small_shapes(timing, dev, kind):
         np.testing.assert_array_equal(gj, wj)
 
 
+@pytest.mark.parametrize("kind", ["normal", "ties", "const", "neg_attn"])
+@pytest.mark.parametrize("shapes", [
+    [(1, 1), (1, 7), (9, 1), (2, 2), (5, 3), (31, 33), (32, 32), (33, 31), (36, 145), (41, 150), (64, 17), (65, 200)],  # staged, one warp
+    [(100, 100), (17, 1500), (7, 400)],            # long rows: more than 32 consecutive time steps per text row
+    [(401, 1500), (445, 1500), (130, 90)],         # few long problems: several warps per problem
+    [(200, 1500)] * 2 + [(129, 300)] * 60,         # many long problems: one warp each, cost matrix not staged
+])
+def test_dtw_jump_only_mode_matches_the_path(timing, dev, kind, shapes):
+    """The product path asks for jump frames only and takes the warp-wide backtrace (one ballot per text row); the
+    frames and the path length must be those of the point-by-point walk of upstream `backtrace` (timing.py:102-113)."""
+    from oracle import dtw as odtw
+    from whisper_char_alignment_b200 import _cabi
+
+    rng = np.random.default_rng(23)
+    costs = [rand_cost(rng, n, m, kind) for n, m in shapes]
+    flat = torch.from_numpy(np.concatenate([c.ravel() for c in costs])).to(dev)
+    recs = np.zeros(len(costs), dtype=_cabi.UTT_DTYPE)
+    moff = joff = 0
+    for b, c in enumerate(costs):
+        n, m = c.shape
+        recs[b]["n_tokens"], recs[b]["n_frames"], recs[b]["row_begin"], recs[b]["row_end"] = n, m, 0, n
+        recs[b]["matrix_off"], recs[b]["jump_off"] = moff, joff
+        moff += n * m
+        joff += n
+    d_utts = _cabi.upload_utts(recs, dev)
+    max_rows, max_frames = int(recs["row_end"].max()), int(recs["n_frames"].max())
+    jumps = torch.full((joff,), -7, dtype=torch.int32, device=dev)
+    plen = torch.zeros(len(costs), dtype=torch.int32, device=dev)
+    nbytes = _cabi.dtw_workspace_bytes(len(costs), max_rows, max_frames)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev) if nbytes else None
+    _cabi.dtw_align(flat.data_ptr(), d_utts, len(costs), max_rows, max_frames, False, path_len=plen, jump_frames=jumps,
+                    trace_ws=ws)
+    jumps, plen = jumps.cpu().numpy(), plen.cpu().numpy()
+    seen = set()
+    for b, c in enumerate(costs):
+        if c.shape in seen:
+            continue  # the C oracle walks 600 k cells per long problem: one of each shape is enough
+        seen.add(c.shape)
+        wi, wj = odtw.dtw_path(c)
+        o = int(recs[b]["jump_off"])
+        np.testing.assert_array_equal(jumps[o:o + c.shape[0]], odtw.jump_frames(wi, wj), err_msg=f"problem {b} {c.shape}")
+        assert plen[b] == len(wi), (b, c.shape)
+
+
 def test_dtw_bit_exact_full_size_and_properties(timing, dev):
     """BASELINE.json config 3 sizes (N=401, M=1500) and the largest legal problem (445 x 1500)."""
     from oracle import dtw as odtw
