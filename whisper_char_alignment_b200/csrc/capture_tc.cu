@@ -815,10 +815,29 @@ int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_la
     cfg.attrs = attr;
     cfg.numAttrs = 1;
 
+    // A persistent grid must be co-resident: clusters cannot straddle GPCs, so fewer clusters of 4 / 8 CTAs fit than
+    // sm_count / csize (16 of 8 on a B200, not 18) and the surplus ones would run as a second wave after the first has
+    // walked its whole tile list - twice the time.  Ask the runtime how many fit and size the grid to that.
 #define WCA_GO(Wv)                                                                                              \
     do {                                                                                                        \
         WCA_CUDA(cudaFuncSetAttribute(tc::capture_tc_kernel<Wv>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                       tc::kSmemBytes));                                                         \
+        if (csize > 1) {                                                                                        \
+            static int fit[4] = {0, 0, 0, 0}; /* per cluster size 1, 2, 4, 8; same device assumed per process */ \
+            const int slot = csize == 2 ? 1 : (csize == 4 ? 2 : 3);                                             \
+            if (fit[slot] == 0) {                                                                               \
+                int n = 0;                                                                                      \
+                if (cudaOccupancyMaxActiveClusters(&n, tc::capture_tc_kernel<Wv>, &cfg) != cudaSuccess || n < 1) { \
+                    (void)cudaGetLastError();                                                                   \
+                    n = sm_count / csize;                                                                       \
+                }                                                                                               \
+                fit[slot] = n;                                                                                  \
+            }                                                                                                   \
+            if (clusters > fit[slot]) {                                                                         \
+                clusters = fit[slot];                                                                           \
+                cfg.gridDim = dim3((unsigned)(clusters * csize));                                               \
+            }                                                                                                   \
+        }                                                                                                       \
         WCA_CUDA(cudaLaunchKernelEx(&cfg, tc::capture_tc_kernel<Wv>, maps, a));                                 \
     } while (0)
     switch (width) {
