@@ -32,6 +32,7 @@
 #include <cuda.h>  // CUtensorMap and its enums only; the encoder is fetched from the driver at run time
 
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -760,19 +761,54 @@ int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_la
         }
         encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
-    tc::TensorMaps maps;
-    memset(&maps, 0, sizeof(maps));
+    // The descriptors only depend on the operand buffers (base pointers, rows, pitch), not on the utterances of the launch:
+    // the launches of one batch (one per cluster-size bucket) and, with a caching allocator, of consecutive batches reuse
+    // them.  144 cuTensorMapEncodeTiled calls cost 0.15-0.3 ms of host time per launch, which the GPU spent idle between
+    // the bucket launches of a LibriSpeech-shaped step.  One entry, guarded by a mutex (the entry points stay thread-safe).
+    struct MapKey {
+        const float *q[WCA_MAX_LAYERS], *k[WCA_MAX_LAYERS];
+        int64_t ld_q, ld_k, q_rows, k_rows;
+        int n_layers, n_heads;
+    };
+    static std::mutex cache_mutex;
+    static MapKey cache_key;
+    static tc::TensorMaps cache_maps;
+    static bool cache_valid = false;
+    MapKey key;
+    memset(&key, 0, sizeof(key));
     for (int l = 0; l < n_layers; ++l) {
-        for (int v = 0; v < 2; ++v) {
-            const int rc = encode_map(encode, &maps.q[v][l], h_q_layers[l], q_rows, (int64_t)n_heads * kHeadDim, ld_q,
-                                      (v + 1) * tc::kStageRows);
-            if (rc) return rc;
+        key.q[l] = h_q_layers[l];
+        key.k[l] = h_k_layers[l];
+    }
+    key.ld_q = ld_q; key.ld_k = ld_k; key.q_rows = q_rows; key.k_rows = k_rows;
+    key.n_layers = n_layers; key.n_heads = n_heads;
+    tc::TensorMaps maps;
+    bool hit = false;
+    {
+        std::lock_guard<std::mutex> lock(cache_mutex);
+        if (cache_valid && memcmp(&key, &cache_key, sizeof(key)) == 0) {
+            memcpy(&maps, &cache_maps, sizeof(maps));
+            hit = true;
         }
-        for (int v = 0; v < 4; ++v) {
-            const int rc = encode_map(encode, &maps.k[v][l], h_k_layers[l], k_rows, (int64_t)n_heads * kHeadDim, ld_k,
-                                      (v + 1) * tc::kStageRows);
-            if (rc) return rc;
+    }
+    if (!hit) {
+        memset(&maps, 0, sizeof(maps));
+        for (int l = 0; l < n_layers; ++l) {
+            for (int v = 0; v < 2; ++v) {
+                const int rc = encode_map(encode, &maps.q[v][l], h_q_layers[l], q_rows, (int64_t)n_heads * kHeadDim, ld_q,
+                                          (v + 1) * tc::kStageRows);
+                if (rc) return rc;
+            }
+            for (int v = 0; v < 4; ++v) {
+                const int rc = encode_map(encode, &maps.k[v][l], h_k_layers[l], k_rows, (int64_t)n_heads * kHeadDim, ld_k,
+                                          (v + 1) * tc::kStageRows);
+                if (rc) return rc;
+            }
         }
+        std::lock_guard<std::mutex> lock(cache_mutex);
+        memcpy(&cache_key, &key, sizeof(key));
+        memcpy(&cache_maps, &maps, sizeof(maps));
+        cache_valid = true;
     }
     int csize = 1;
     while (csize < 8 && ((((max_frames + csize - 1) / csize) + 15) & ~15) > tc::kMaxOwn) csize *= 2;
