@@ -165,3 +165,56 @@ def test_greedy_decode_runs_on_cpu_and_stops_at_eot(tokenizer):
     assert len(both) == 2 and both[0] == one
     for toks in both:
         assert len(toks) <= 6 and all(0 <= t < tokenizer.eot for t in toks)
+
+
+# ---------------------------------------------------------------- warp-wide backtrace (csrc/dtw.cu), modelled on the host
+def _walk_point_by_point(trace):
+    """upstream whisper.timing.backtrace on a (N+1, M+1) trace with its border rule; returns (jump frames, path length)."""
+    n, m = trace.shape[0] - 1, trace.shape[1] - 1
+    jump = np.full(n, -1, dtype=np.int64)
+    i, j, length = n, m, 0
+    while i > 0 or j > 0:
+        length += 1
+        code = 1 if j == 0 else (2 if i == 0 else int(trace[i, j]))
+        if code != 2 and i >= 1:
+            jump[i - 1] = j - 1
+        if code == 0:
+            i, j = i - 1, j - 1
+        elif code == 1:
+            i -= 1
+        else:
+            j -= 1
+    return jump, length
+
+
+def _walk_row_by_row(trace, lanes=32):
+    """What the kernel does on the jump-only path: per text row, look at `lanes` cells to the left, take the nearest one
+    whose step leaves the row (a ballot + find-first-set), move up from there; path length = N + M - diagonal steps."""
+    n, m = trace.shape[0] - 1, trace.shape[1] - 1
+    jump = np.full(n, -1, dtype=np.int64)
+    row, col, n_diag = n - 1, m - 1, 0
+    while row >= 0 and col >= 0:
+        window = [int(trace[row + 1, col - k + 1]) if col - k >= 0 else 2 for k in range(lanes)]
+        leaves = [k for k, c in enumerate(window) if c != 2]
+        if not leaves:
+            col -= lanes
+            continue
+        k = leaves[0]
+        jump[row] = col - k
+        n_diag += window[k] == 0
+        col -= k + (window[k] == 0)
+        row -= 1
+    return jump, n + m - n_diag
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_row_by_row_backtrace_equals_the_point_by_point_walk(seed):
+    rng = np.random.default_rng(seed)
+    for n, m in [(1, 1), (1, 40), (9, 1), (5, 3), (41, 150), (36, 145), (7, 400), (64, 17)]:
+        # long runs of time steps (code 2) so that windows without a row change occur, and all three codes at the borders
+        p2 = [0.34, 0.8, 0.97][seed % 3]
+        trace = rng.choice(3, size=(n + 1, m + 1), p=[(1 - p2) / 2, (1 - p2) / 2, p2])
+        want_jump, want_len = _walk_point_by_point(trace)
+        got_jump, got_len = _walk_row_by_row(trace)
+        np.testing.assert_array_equal(got_jump, want_jump, err_msg=f"{n}x{m}")
+        assert got_len == want_len, (n, m)
