@@ -32,7 +32,7 @@ import timing as ref_timing  # noqa: E402  (the reference's own module)
 from whisper.audio import log_mel_spectrogram, pad_or_trim  # noqa: E402
 from whisper.tokenizer import get_tokenizer  # noqa: E402
 
-from oracle.synth import make_mel, make_model  # noqa: E402
+from oracle.synth import long_text, make_mel, make_model  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -49,6 +49,58 @@ CASES = [
     dict(name="mini_char_topk", model="mini", text="whisper has an internal word aligner", unit="char", aggr="topk", topk=5, width=3, qk_scale=1.0, frames=211),
     dict(name="mini_sub_mean", model="mini", text="whisper has an internal word aligner", unit="subword", aggr="mean", topk=-1, width=7, qk_scale=1.0, frames=211),
 ]
+
+
+# Large shapes (BASELINE.json configs[2] class: T ~ 400, F up to 1500): the full (L,H,T,F) maps would be tens of MB,
+# so the fixture keeps the cost matrix, the path, the times and the scores in full and the maps as a strided sample
+# plus per-head digests (column sums, row arg-max, sum of squares).  The mel is re-created from its seed.
+LARGE_CASES = [
+    dict(name="long_char_topk", model="long", n_chars=398, text_seed=41, unit="char", aggr="topk", topk=5, width=3,
+         qk_scale=1.0, frames=1500, mel_seed=501),
+    dict(name="long_char_mean_w7", model="long", n_chars=190, text_seed=42, unit="char", aggr="mean", topk=-1, width=7,
+         qk_scale=1.0, frames=1100, mel_seed=502),
+]
+from oracle.gen_golden_digests import large_digests  # noqa: E402
+
+
+def run_large_case(c, model, tk):
+    c = dict(c)
+    c["text"] = long_text(c["n_chars"], c["text_seed"])
+    mel = make_mel(model.dims.n_mels, 2 * model.dims.n_audio_ctx, 2 * c["frames"], seed=c["mel_seed"])
+    text_tokens = ref_retok.encode(c["text"], tk, c["unit"])
+    tokens = torch.tensor([*tk.sot_sequence, tk.no_timestamps, *text_tokens, tk.eot])
+    assert len(tokens) <= 448
+    w, logits = ref_timing.get_attentions(mel, tokens, model, tk, c["frames"], c["width"], c["qk_scale"])
+    words, st, en, matrix, scores = ref_timing.force_align(w, text_tokens, tk, c["unit"], c["aggr"], c["topk"])
+    from whisper.timing import dtw
+    ti, tj = dtw(-matrix)
+    out = dict(
+        tokens=tokens.numpy(), text_tokens=np.array(text_tokens, dtype=np.int64),
+        mel_digest=np.array([mel.double().sum().item(), mel.abs().double().sum().item()]),
+        logits_digest=np.array([logits.double().sum().item(), logits.abs().double().sum().item()]),
+        weights_shape=np.array(w.shape), sentinel=np.array(False),
+        start_times=st, end_times=en, matrix=matrix.numpy(), words=np.array(json.dumps(words)),
+        path_text=ti.astype(np.int32), path_time=tj.astype(np.int32), case=np.array(json.dumps(c)),
+        **large_digests(w.numpy()),
+    )
+    if scores is not None:
+        out.update(score_values=np.array([s[0] for s in scores], dtype=np.float64),
+                   score_heads=np.array([s[1] for s in scores], dtype=np.int64))
+        # every head's score, not only the selected ones (pins the ranking)
+        _, all_scores = ref_timing.filter_attention(w, 10 ** 6)
+        out.update(all_score_values=np.array([s[0] for s in all_scores], dtype=np.float64),
+                   all_score_heads=np.array([s[1] for s in all_scores], dtype=np.int64))
+    return out
+
+
+def main_large():
+    os.makedirs(OUT, exist_ok=True)
+    tk = get_tokenizer(True, language="English")
+    for c in LARGE_CASES:
+        model = make_model(c["model"], 0, 4.0)
+        out = run_large_case(c, model, tk)
+        np.savez_compressed(os.path.join(OUT, "large_" + c["name"] + ".npz"), **out)
+        print("large_" + c["name"], out["weights_shape"], out["matrix"].shape, out["start_times"][:5], len(out["path_text"]))
 
 
 def sphere_pcm(path):
@@ -136,5 +188,22 @@ def main():
     print(c["name"], out["weights"].shape, out["start_times"], out["end_times"])
 
 
+def main_pcm():
+    """The PCM of the C1 case (sample/test.wav, NIST SPHERE, 46592 int16 samples) so that the audio front-end of
+    the product (audio.read_audio is tested on synthetic SPHERE files; audio.log_mel_spectrogram here) can be checked
+    against the mel the C1 fixture was generated from, without /root/reference at test time."""
+    raw = open(os.path.join(REF, "sample", "test.wav"), "rb").read()
+    hdr = int(raw[8:16].split()[0])
+    pcm16 = np.frombuffer(raw[hdr:], dtype="<i2").copy()
+    np.savez_compressed(os.path.join(OUT, "aux_c1_pcm.npz"), pcm16=pcm16)
+    print("aux_c1_pcm", pcm16.shape)
+
+
 if __name__ == "__main__":
-    main()
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "pcm"):
+        main_pcm()
+    if which in ("all", "small"):
+        main()
+    if which in ("all", "large"):
+        main_large()

@@ -82,18 +82,19 @@ def test_eval_ali_on_a_handmade_prediction_file(tmp_path):
 @pytest.mark.gpu
 def test_infer_eval_probe_end_to_end_on_synthetic_data(tmp_path):
     out = tmp_path / "run"
-    res = infer_ali.main(["--model", "micro", "--dataset", "synthetic", "--scp", "timit:10", "--output_dir", str(out),
+    res = infer_ali.main(["--model", "random:micro", "--dataset", "synthetic", "--scp", "timit:10", "--output_dir", str(out),
                           "--aggr", "topk", "--topk", "2", "--aligned_unit_type", "char", "--medfilt_width", "3",
                           "--tolerance", "0.5", "--save_prediction", "--batch_size", "4", "--strict"])
     assert set(res) == {"precision", "recall", "f1", "r_value"} and 0.0 <= res["f1"] <= 1.0
     dumped = json.load(open(glob.glob(str(out / "*.json"))[0]))
     assert dumped["aggr"] == "topk" and "f1" in dumped
+    assert dumped["model_source"].startswith("random-init:micro") and "ground-truth" in dumped["transcript_source"]
     pkl = glob.glob(str(out / "*-predictions.pkl"))[0]
     again = eval_ali.main(["--pred", pkl, "--tolerance", "0.5"])
     assert abs(again["f1"] - res["f1"]) < 1e-9  # same counts at the same tolerance
-    base = infer_ali.main(["--model", "micro", "--dataset", "synthetic", "--scp", "timit:4", "--output_dir", str(out),
+    base = infer_ali.main(["--model", "random:micro", "--dataset", "synthetic", "--scp", "timit:4", "--output_dir", str(out),
                            "--default_whisper_timing", "--tolerance", "0.5"])
     assert 0.0 <= base["recall"] <= 1.0
-    probe = probe_oracle.main(["--model", "micro", "--dataset", "synthetic", "--scp", "probe:3", "--output_dir", str(out),
+    probe = probe_oracle.main(["--model", "random:micro", "--dataset", "synthetic", "--scp", "probe:3", "--output_dir", str(out),
                                "--aligned_unit_type", "char", "--medfilt_width", "3", "--tolerance", "0.5", "--hit_within", "2"])
     assert probe["utterances_probed"] == 3 and 0.0 <= probe["hit_rate"] <= 1.0

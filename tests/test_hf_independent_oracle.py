@@ -102,3 +102,15 @@ def test_product_greedy_decode_agrees_with_hf_greedy(oracle_models, hf_models, t
     want = hf_crosscheck.hf_greedy(hf_models("micro"), mel, [*tokenizer.sot_sequence, tokenizer.no_timestamps],
                                    tokenizer.eot, 12)
     assert got == want
+
+
+def test_large_reference_fixture_agrees_with_hf(hf_models):
+    """Same statement at the LibriSpeech-class shape (T = 195, F = 1100 of 1500): sample + digests of the maps the
+    reference produced on the shim, against the independent forward."""
+    from conftest import check_large_maps, load_large
+
+    g = load_large("large_long_char_mean_w7")
+    c = g["case"]
+    probs, _ = hf_crosscheck.hf_forward(hf_models(c["model"]), torch.from_numpy(g["mel"]), torch.from_numpy(g["tokens"]))
+    maps = hf_crosscheck.maps_from_probabilities(probs, c["frames"], c["width"], c["qk_scale"]).numpy()
+    check_large_maps(maps, g, 1e-4, "HF vs reference-on-shim, large_long_char_mean_w7")

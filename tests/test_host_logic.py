@@ -218,3 +218,77 @@ def test_row_by_row_backtrace_equals_the_point_by_point_walk(seed):
         got_jump, got_len = _walk_row_by_row(trace)
         np.testing.assert_array_equal(got_jump, want_jump, err_msg=f"{n}x{m}")
         assert got_len == want_len, (n, m)
+
+
+# ------------------------------------------------------------------ round-2 host logic
+def test_large_v3_special_tokens_follow_the_language_count():
+    """large-v3 has 100 language tokens: everything after the language block moves up by one."""
+    v2, v3 = get_tokenizer(True, num_languages=99), get_tokenizer(True, num_languages=100)
+    assert (v2.sot_sequence, v2.no_timestamps, v2.timestamp_begin) == ((50258, 50259, 50359), 50363, 50364)
+    assert (v3.sot_sequence, v3.no_timestamps, v3.timestamp_begin) == ((50258, 50259, 50360), 50364, 50365)
+    assert v3.eot == v2.eot == 50257
+
+
+def test_random_weights_must_be_asked_for_by_name(tmp_path):
+    from whisper_char_alignment_b200 import whisper_model
+
+    with pytest.raises(FileNotFoundError, match="random:medium"):
+        whisper_model.load_model("medium")
+    with pytest.raises(ValueError):
+        whisper_model.load_model("random:large-v2")
+    m = whisper_model.load_model("random:micro", seed=3)
+    assert m.model_source == "random-init:micro:seed3:qk_gain1" and m.dims.n_audio_ctx == 1500
+    path = str(tmp_path / "ckpt.pt")
+    whisper_model.save_checkpoint(m, path)
+    again = whisper_model.load_model(path)
+    assert again.model_source.startswith("checkpoint:")
+    for a, b in zip(m.state_dict().values(), again.state_dict().values()):
+        assert torch.equal(a.to_dense() if a.is_sparse else a, b.to_dense() if b.is_sparse else b)
+
+
+def test_empty_transcription_stays_empty_like_the_reference(tokenizer):
+    """infer_ali.py:65 `len(transcription) == ''` never fires, so an empty transcript reaches force_align as
+    [eot] only and yields the sentinel; the CLI must not turn it into a space token."""
+    from whisper_char_alignment_b200.cli import common
+
+    record = (None, torch.zeros(80, 3000), 32000, "", [], [], "empty")
+    item = common.prepare(record, tokenizer, "subword", "cpu", None, None)
+    assert item["text_tokens"] == [] and item["tokens"].tolist()[-2:] == [tokenizer.no_timestamps, tokenizer.eot]
+
+
+# ------------------------------------------------------------------ audio front-end (row f3)
+def _c1_pcm():
+    from conftest import GOLDEN_DIR
+
+    return np.load(os.path.join(GOLDEN_DIR, "aux_c1_pcm.npz"))["pcm16"].astype(np.float32) / 32768.0
+
+
+def test_log_mel_reproduces_the_mel_of_the_c1_reference_fixture():
+    """dataset.py:46-48 of the reference: log_mel_spectrogram(pad_or_trim(audio), n_mels).  The C1 fixture's mel came
+    from the restated upstream front-end on sample/test.wav; the product's front-end on the same PCM gives it back."""
+    from conftest import load_golden
+    from whisper_char_alignment_b200 import audio
+
+    g = load_golden("c1_base_sample")
+    pcm = _c1_pcm()
+    assert len(pcm) == int(g["n_samples"]) == 46592 and len(pcm) // audio.N_SAMPLES_PER_TOKEN == g["case"]["frames"]
+    mel = audio.log_mel_spectrogram(audio.pad_or_trim(torch.from_numpy(pcm)), 80)
+    assert mel.shape == (80, 3000)
+    np.testing.assert_allclose(mel.numpy(), g["mel"], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_log_mel_agrees_with_the_hf_feature_extractor(n_mels):
+    """An independent implementation of the Whisper front-end (transformers' numpy WhisperFeatureExtractor: its own
+    Slaney filterbank and STFT) on the same PCM: 80 mels (base/medium) and 128 mels (large-v3)."""
+    transformers = pytest.importorskip("transformers")
+    from whisper_char_alignment_b200 import audio
+
+    pcm = _c1_pcm()
+    fe = transformers.WhisperFeatureExtractor(feature_size=n_mels)
+    want = fe(pcm, sampling_rate=16000, return_tensors="np")["input_features"][0]
+    got = audio.log_mel_spectrogram(audio.pad_or_trim(torch.from_numpy(pcm)), n_mels).numpy()
+    assert got.shape == want.shape == (n_mels, 3000)
+    # log10 of a float32 power spectrum computed by two different FFTs: 1e-4 of the [-1, 1] range on the speech part
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-4)
+    np.testing.assert_allclose(audio.mel_filters(n_mels).numpy(), fe.mel_filters.T, rtol=0, atol=1e-6)

@@ -122,3 +122,35 @@ def test_default_find_alignment_restatement(name, oracle_models, tokenizer):
     np.testing.assert_allclose(weights.numpy(), g["weights"], rtol=2e-4, atol=2e-5)
     np.testing.assert_array_equal(st, g["start_times"])
     np.testing.assert_array_equal(en, g["end_times"])
+
+
+# ------------------------------------------------------------------ large, reference-generated shapes
+from conftest import check_large_maps, large_names, load_large  # noqa: E402
+
+
+@pytest.mark.parametrize("name", large_names())
+def test_restatement_reproduces_large_reference_fixture(name, oracle_models, tokenizer):
+    """T ~ 200-400, F 1100-1500 (BASELINE.json configs[2] class) through the reference's own timing.py: the port
+    regenerates the maps (checked on the stored sample + digests), and from them the same matrix, scores, path
+    and boundaries."""
+    g = load_large(name)
+    c = g["case"]
+    model = oracle_models(c["model"])
+    w, logits = ref_path.get_attentions(torch.from_numpy(g["mel"]), torch.from_numpy(g["tokens"]), model, tokenizer,
+                                        c["frames"], c["width"], c["qk_scale"])
+    check_large_maps(w.numpy(), g, 2e-5, name)
+    np.testing.assert_allclose(logits.double().sum().item(), g["logits_digest"][0], rtol=1e-5)
+    words, st, en, matrix, scores = ref_path.force_align(w, g["text_tokens"].tolist(), tokenizer, c["unit"], c["aggr"], c["topk"])
+    assert words == g["words"]
+    np.testing.assert_allclose(matrix.numpy(), g["matrix"], rtol=2e-5, atol=1e-9)
+    if scores is not None:
+        assert [list(s[1]) for s in scores] == g["score_heads"].tolist()
+        np.testing.assert_allclose([s[0] for s in scores], g["score_values"], rtol=1e-5)
+    # integer work on the STORED matrix: exact
+    ti, tj = odtw.dtw_path(-g["matrix"])
+    np.testing.assert_array_equal(ti, g["path_text"])
+    np.testing.assert_array_equal(tj, g["path_time"])
+    _, wt = ref_path.split_tokens_on_spaces(g["text_tokens"].tolist() + [tokenizer.eot], tokenizer, c["unit"])
+    st2, en2, _ = ref_path.boundaries_from_path(ti, tj, wt)
+    np.testing.assert_array_equal(st2, g["start_times"])
+    np.testing.assert_array_equal(en2, g["end_times"])

@@ -53,3 +53,64 @@ def test_single_process_gather_is_identity():
     got = sharding.gather_alignments({3: ([0.1, 0.2], [0.2, 0.4])})
     assert list(got) == [3] and got[3][1].tolist() == [0.2, 0.4]
     assert sharding.gather_counters(1, 2, 3) == (1, 2, 3)
+
+
+# ------------------------------------------------------------------ cost-balanced shards + length buckets (row f2)
+def _libri_costs(n=2620):
+    from whisper_char_alignment_b200 import batching, synthetic
+    from whisper_char_alignment_b200.tokenizer import get_tokenizer
+
+    tk = get_tokenizer(True, language="English")
+    utts = synthetic.librispeech_shaped(n, tk, seed=2620, with_mel=False)
+    n_tok, n_frm = [len(u.tokens) for u in utts], [u.max_frames for u in utts]
+    return n_tok, n_frm, [batching.utterance_cost(t, f) for t, f in zip(n_tok, n_frm)]
+
+
+def test_lpt_shards_partition_and_balance_the_librispeech_list():
+    """BASELINE.json configs[2]: 2620 utterances of 2-30 s.  Every utterance on exactly one rank, and the modelled
+    cost of the heaviest rank within 1 % of the mean at 2/4/8 ranks (round-robin is measured next to it)."""
+    n_tok, n_frm, costs = _libri_costs()
+    for world in (1, 2, 4, 8):
+        parts = [sharding.shard_by_cost(costs, r, world) for r in range(world)]
+        assert sorted(i for p in parts for i in p) == list(range(len(costs)))
+        assert sharding.shard_imbalance(costs, world, "lpt") < 1.01
+        assert sharding.shard_imbalance(costs, world, "lpt") <= sharding.shard_imbalance(costs, world, "round_robin") + 1e-12
+
+
+def test_length_bucketed_batches_cover_every_kept_utterance_once():
+    from whisper_char_alignment_b200 import batching
+
+    n_tok, n_frm, _ = _libri_costs(500)
+    n_tok[3], n_frm[7] = 449, 1501  # the reference skips these (infer_ali.py:78-81)
+    plan, skipped = batching.plan_batches(n_tok, n_frm, 32)
+    assert sorted(skipped) == [3, 7]
+    flat = [i for b in plan for i in b]
+    assert sorted(flat) == [i for i in range(500) if i not in (3, 7)]
+    assert all(1 <= len(b) <= 32 for b in plan)
+    # the map budget closes a batch early: 4 * 384 * T * F bytes per utterance
+    assert all(sum(4.0 * 384 * n_tok[i] * n_frm[i] for i in b) <= 24e9 or len(b) == 1 for b in plan)
+    # bucketing by length removes most of the decoder padding that batches in list order carry
+    in_order = [list(range(i, min(i + 32, 500))) for i in range(0, 500, 32)]
+    in_order = [[i for i in b if i not in (3, 7)] for b in in_order]
+    assert batching.padding_waste(n_tok, plan) < 0.1 < batching.padding_waste(n_tok, in_order)
+    assert not batching.fits_context(10, 0) and batching.fits_context(448, 1500)
+
+
+def _lpt_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _, _, costs = _libri_costs(301)
+        mine = sharding.shard_by_cost(costs, rank, world)
+        merged = sharding.gather_alignments({i: (np.array([costs[i]]), np.array([float(i)])) for i in mine})
+        assert sorted(merged) == list(range(301))  # the ranks' shards are disjoint and complete
+        tot = sharding.gather_counters(len(mine), 0, 0)
+        assert tot[0] == 301
+        open(os.path.join(out_dir, f"lpt{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_lpt_shards_meet_in_one_gather(tmp_path):
+    mp.spawn(_lpt_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert all((tmp_path / f"lpt{r}").exists() for r in range(2))

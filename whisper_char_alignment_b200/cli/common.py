@@ -16,16 +16,11 @@ MAX_FRAMES = 1500  # reference infer_ali.py:25
 MAX_LENGTH = 448   # reference infer_ali.py:26
 AUDIO_SAMPLES_PER_TOKEN = audio.N_SAMPLES_PER_TOKEN  # reference infer_ali.py:179
 
-TEST_SIZES = {  # tiny dims for smoke runs: 30 s context and head width 64 like the published models
-    "micro": (80, 1500, 128, 2, 2, 51865, 448, 128, 2, 2),
-    "mini": (80, 1500, 256, 4, 2, 51865, 448, 256, 4, 3),
-}
-
-
 def load_model_and_tokenizer(name: str, device, qk_gain: float = 4.0):
-    """Stock `openai-whisper` when it is installed (real checkpoints, real tokenizer, greedy
-    decode available); otherwise a checkpoint path or a seeded random-init model of the named
-    size with the offline byte tokenizer."""
+    """Stock `openai-whisper` when it is installed (real checkpoints, real tokenizer, greedy decode available).
+    Otherwise `name` must be a checkpoint file or an explicit `random:<size>` (seeded random init, offline byte
+    tokenizer) -- a bare size name such as `medium` raises instead of silently aligning with random weights.
+    Returns (model, tokenizer, whisper package or None, model_source)."""
     try:
         import whisper  # noqa: F401
         from whisper.tokenizer import get_tokenizer
@@ -33,16 +28,22 @@ def load_model_and_tokenizer(name: str, device, qk_gain: float = 4.0):
         if not (hasattr(whisper, "decode") and hasattr(whisper, "DecodingOptions")):
             raise ImportError("a `whisper` module without decode() is not openai-whisper")
         model = whisper.load_model(name).to(device)
-        return model, get_tokenizer(model.is_multilingual, language="English"), whisper
+        return model, get_tokenizer(model.is_multilingual, language="English"), whisper, f"openai-whisper:{name}"
     except ImportError:
-        if name in TEST_SIZES:
-            model = whisper_model.random_init(whisper_model.ModelDimensions(*TEST_SIZES[name]), qk_gain=qk_gain).to(device)
-        else:
-            model = whisper_model.load_model(name, device, qk_gain=qk_gain)
-        return model, byte_tokenizer(model.is_multilingual, language="English"), None
+        model = whisper_model.load_model(name, device, qk_gain=qk_gain)
+        # the reference leaves num_languages at 99 (infer_ali.py:41), which is off by one for large-v3's
+        # vocabulary; the offline tokenizer takes the model's own count
+        tk = byte_tokenizer(model.is_multilingual, language="English", num_languages=model.num_languages)
+        return model, tk, None, model.model_source
 
 
 TRANSCRIBE = os.environ.get("WCA_TRANSCRIBE", "reference")  # offline default: align the reference transcript
+
+
+def transcript_source(whisper_pkg) -> str:
+    if whisper_pkg is not None:
+        return "whisper.decode"
+    return "greedy_decode" if TRANSCRIBE == "greedy" else "ground-truth transcript (no ASR step)"
 
 
 def transcribe(whisper_pkg, model, mel, reference_text: str, tokenizer=None) -> str:
@@ -62,7 +63,9 @@ def prepare(record, tokenizer, unit, device, whisper_pkg, model):
     _, mel, duration, text, starts, ends, fid = record
     mel = mel.to(device)
     text = remove_punctuation(text)
-    transcription = remove_punctuation(transcribe(whisper_pkg, model, mel, text, tokenizer)) or " "
+    # an empty transcription stays empty, as in the reference (its `len(transcription) == ''` guard at
+    # infer_ali.py:65 never fires): force_align then returns the EOT-only sentinel and 0 predictions
+    transcription = remove_punctuation(transcribe(whisper_pkg, model, mel, text, tokenizer))
     text_tokens = encode(transcription, tokenizer, unit)
     tokens = torch.tensor([*tokenizer.sot_sequence, tokenizer.no_timestamps, *text_tokens, tokenizer.eot], device=device)
     max_frames = int(duration) // AUDIO_SAMPLES_PER_TOKEN

@@ -44,7 +44,7 @@ def infer_dataset(args):
     print(args)
     device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(device)
-    model, tokenizer, whisper_pkg = common.load_model_and_tokenizer(args.model, device)
+    model, tokenizer, whisper_pkg, model_source = common.load_model_and_tokenizer(args.model, device)
     dataset = DATASET[args.dataset](args.scp, n_mels=args.n_mels, device=device)
     corrects = total_preds = total_gts = includes_best = n_probed = 0
     for n in range(len(dataset)):
@@ -55,9 +55,8 @@ def infer_dataset(args):
         if it is None:
             continue
         w, _ = timing.get_attentions(it["mel"], it["tokens"], model, tokenizer, it["max_frames"], args.medfilt_width, 1.0)
-        maps, scores = timing.filter_attention(w, topk=N_PROBED_HEADS)
-        outs = timing.force_align_batch([m.unsqueeze(0) for m in maps], [it["text_tokens"]] * len(maps), tokenizer,
-                                        aligned_unit_type=args.aligned_unit_type, aggregation="mean", topk=1)
+        outs, scores = timing.probe_heads_batch([w], [it["text_tokens"]], tokenizer, args.aligned_unit_type,
+                                                N_PROBED_HEADS)[0]
         ref_words = it["text"].split()
         best_f1, best_ends, best_words, best_score = -1.0, None, None, None
         for out, score in zip(outs, scores):
@@ -88,7 +87,8 @@ def infer_dataset(args):
     results = dict(precision=precision, recall=recall, f1=f1, r_value=r_value,
                    hit_rate=includes_best / max(len(dataset), 1), utterances_probed=n_probed)
     print(results)
-    common.dump_results(args, results)
+    common.dump_results(args, {**results, "model_source": model_source,
+                               "transcript_source": common.transcript_source(whisper_pkg)})
     return results
 
 

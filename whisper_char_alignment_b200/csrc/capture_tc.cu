@@ -31,6 +31,7 @@
 //                                       alternating tiles (accumulator i & 1)
 #include <cuda.h>  // CUtensorMap and its enums only; the encoder is fetched from the driver at run time
 
+#include <atomic>
 #include <cstring>
 #include <mutex>
 
@@ -764,12 +765,15 @@ int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_la
     // The descriptors only depend on the operand buffers (base pointers, rows, pitch), not on the utterances of the launch:
     // the launches of one batch (one per cluster-size bucket) and, with a caching allocator, of consecutive batches reuse
     // them.  144 cuTensorMapEncodeTiled calls cost 0.15-0.3 ms of host time per launch, which the GPU spent idle between
-    // the bucket launches of a LibriSpeech-shaped step.  One entry, guarded by a mutex (the entry points stay thread-safe).
+    // the bucket launches of a LibriSpeech-shaped step.  One entry, keyed by the device and the operand buffers, guarded by a
+    // mutex (the entry points stay thread-safe; threads driving different devices only evict each other's entry).
     struct MapKey {
         const float *q[WCA_MAX_LAYERS], *k[WCA_MAX_LAYERS];
         int64_t ld_q, ld_k, q_rows, k_rows;
-        int n_layers, n_heads;
+        int n_layers, n_heads, device;
     };
+    int device = 0;
+    WCA_CUDA(cudaGetDevice(&device));
     static std::mutex cache_mutex;
     static MapKey cache_key;
     static tc::TensorMaps cache_maps;
@@ -781,7 +785,7 @@ int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_la
         key.k[l] = h_k_layers[l];
     }
     key.ld_q = ld_q; key.ld_k = ld_k; key.q_rows = q_rows; key.k_rows = k_rows;
-    key.n_layers = n_layers; key.n_heads = n_heads;
+    key.n_layers = n_layers; key.n_heads = n_heads; key.device = device;
     tc::TensorMaps maps;
     bool hit = false;
     {
@@ -859,7 +863,8 @@ int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_la
         WCA_CUDA(cudaFuncSetAttribute(tc::capture_tc_kernel<Wv>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                       tc::kSmemBytes));                                                         \
         if (csize > 1) {                                                                                        \
-            static int fit[4] = {0, 0, 0, 0}; /* per cluster size 1, 2, 4, 8; same device assumed per process */ \
+            static std::atomic<int> fit_tab[64][4]; /* [device][cluster size 1, 2, 4, 8], zero-initialised */  \
+            std::atomic<int> *fit = fit_tab[device & 63];                                                       \
             const int slot = csize == 2 ? 1 : (csize == 4 ? 2 : 3);                                             \
             if (fit[slot] == 0) {                                                                               \
                 int n = 0;                                                                                      \

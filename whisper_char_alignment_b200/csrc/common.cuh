@@ -62,6 +62,13 @@ __device__ __forceinline__ float ld_stream(const float *p) {
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
+// Same cache policy through the coherent path: for rows a kernel may later overwrite in place (ld.global.nc is only
+// defined for memory that stays read-only for the whole kernel).
+__device__ __forceinline__ float ld_stream_coherent(const float *p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ float4 ld_stream4(const float4 *p) {
     float4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"

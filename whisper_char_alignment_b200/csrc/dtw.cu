@@ -414,7 +414,17 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_multi_kernel(const DtwLaun
         float up_top = __shfl_up_sync(0xffffffffu, left[R - 1], 1);
         if (lane == 0) {
             up_top = INFINITY;  // cost[0][j], j >= 1 (first warp)
-            if (warp > 0 && act) up_top = __uint_as_float((uint32_t)edge_in[c]);  // published: checked above
+            if (warp > 0 && act) {
+                // every word carries its own column tag: the group poll above saw the LAST column of the group, and
+                // stores to different addresses need not become visible in program order, so the tag of THIS word is
+                // checked too (it is almost always already there: no back-off)
+                unsigned long long w = edge_in[c];
+                for (uint32_t spins = 0; (uint32_t)(w >> 32) != (uint32_t)(c + 1); ++spins) {
+                    if (spins > (1u << 24)) __trap();
+                    w = edge_in[c];
+                }
+                up_top = __uint_as_float((uint32_t)w);
+            }
         }
         float xc[R];
 #pragma unroll

@@ -26,13 +26,14 @@ __device__ __forceinline__ float median_at(const float *padded, int f, int width
     }
 }
 
-// `in` may alias `out` (the row is fully staged in shared memory before any store).
+// `in` may alias `out` (the row is fully staged in shared memory before any store; the loads therefore use the
+// coherent ld.global.cg path, not ld.global.nc).
 // padded: F + 2*half floats, filtered: F floats, both private to this warp.
 template <int W>
 __device__ __forceinline__ void filter_softmax_row(const float *in, float *out, int F, int width, float qk_scale,
                                                    float *padded, float *filtered, int lane) {
     const int half = (F <= width / 2) ? 0 : width / 2;  // identity filter for very short rows
-    for (int f = lane; f < F; f += kWarp) padded[half + f] = ld_stream(in + f);
+    for (int f = lane; f < F; f += kWarp) padded[half + f] = ld_stream_coherent(in + f);
     __syncwarp();
     // reflect halo (no edge repeat): left i -> x[i+1 .. half], right -> x[F-2 ...]
     for (int i = lane; i < half; i += kWarp) {

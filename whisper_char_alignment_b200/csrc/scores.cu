@@ -127,13 +127,19 @@ __global__ void __launch_bounds__(256) head_scores_kernel(const float *__restric
 }
 
 // grid (n_utts), block 256, dynamic smem n_heads floats.  Rank by counting with the
-// reference's tuple order (score, layer, head): ties go to the smaller head index.
+// reference's tuple order (score, layer, head): ties go to the smaller head index.  The order must be TOTAL so that
+// every output slot is written exactly once: a NaN score (non-finite logits upstream) compares false both ways and
+// would give several heads the same rank, leaving `sel` slots uninitialised for aggregate_heads_kernel to
+// dereference.  NaN ranks below every number (the reference's sorted() leaves NaN order unspecified).
 __global__ void __launch_bounds__(256) topk_heads_kernel(const float *__restrict__ scores,
                                                          const wca_utt_t *__restrict__ utts, int n_heads,
                                                          int32_t *__restrict__ sel, float *__restrict__ sel_scores) {
     extern __shared__ float s_sc[];
     const wca_utt_t u = utts[blockIdx.x];
-    for (int i = threadIdx.x; i < n_heads; i += blockDim.x) s_sc[i] = scores[u.score_off + i];
+    for (int i = threadIdx.x; i < n_heads; i += blockDim.x) {
+        const float v = scores[u.score_off + i];
+        s_sc[i] = (v != v) ? -INFINITY : v;  // ranking key; the reported score stays the original value
+    }
     __syncthreads();
     const int n_sel = u.n_sel < n_heads ? u.n_sel : n_heads;
     const int first = n_heads - n_sel;
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(256) topk_heads_kernel(const float *__restrict
         }
         if (rank >= first) {
             sel[u.sel_off + rank - first] = i;
-            if (sel_scores) sel_scores[u.sel_off + rank - first] = si;
+            if (sel_scores) sel_scores[u.sel_off + rank - first] = scores[u.score_off + i];
         }
     }
 }

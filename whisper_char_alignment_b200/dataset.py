@@ -40,6 +40,12 @@ class TIMIT(torch.utils.data.Dataset):
             words.append(w)
         return " ".join(words), starts, ends
 
+    def size_hint(self, i):
+        """(approximate token count, approximate frame count) without decoding the audio: for cost-balanced
+        sharding and length bucketing (16-bit mono PCM behind a 1024-byte SPHERE header; ~14 characters/s)."""
+        n_samples = max(os.path.getsize(self.items[i][1]) - 1024, 0) // 2
+        return int(14 * n_samples / audio.SAMPLE_RATE) + 5, n_samples // audio.N_SAMPLES_PER_TOKEN
+
     def __getitem__(self, i):
         fid, wav, wrd = self.items[i]
         pcm, rate = audio.read_audio(wav)
@@ -74,6 +80,11 @@ class LibriSpeech(torch.utils.data.Dataset):
     def __len__(self):
         return len(self.items)
 
+    def size_hint(self, i):
+        """From the transcript alone (FLAC is not decoded here): characters, and frames at ~14 characters/s."""
+        n_chars = len(self.items[i][2])
+        return n_chars + 5, int(n_chars / 14.0 * audio.TOKENS_PER_SECOND)
+
     def __getitem__(self, i):
         import soundfile
 
@@ -106,6 +117,9 @@ class Synthetic(torch.utils.data.Dataset):
 
     def __len__(self):
         return len(self.utts)
+
+    def size_hint(self, i):
+        return len(self.utts[i].tokens), self.utts[i].max_frames
 
     def __getitem__(self, i):
         u = self.utts[i]

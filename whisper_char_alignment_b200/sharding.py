@@ -15,6 +15,33 @@ def shard_indices(n_items: int, rank: int, world_size: int):
     return list(range(rank, n_items, world_size))
 
 
+def shard_by_cost(costs, rank: int, world_size: int):
+    """Longest-processing-time-first assignment of items with very unequal cost (LibriSpeech: 2-30 s utterances,
+    BASELINE.json configs[2]): items in decreasing cost, each to the currently lightest rank.  Deterministic and
+    identical on every rank (ties by index); every item belongs to exactly one rank.  Returns this rank's indices in
+    increasing order.  The greedy bound is 4/3 - 1/(3W) of the optimum; with hundreds of items per rank the measured
+    imbalance is well under 1 %."""
+    order = sorted(range(len(costs)), key=lambda i: (-float(costs[i]), i))
+    loads = [0.0] * world_size
+    mine = []
+    for i in order:
+        r = min(range(world_size), key=lambda k: (loads[k], k))
+        loads[r] += float(costs[i])
+        if r == rank:
+            mine.append(i)
+    return sorted(mine)
+
+
+def shard_imbalance(costs, world_size: int, how: str = "lpt") -> float:
+    """max over ranks of the assigned cost / mean, for `how` in {"lpt", "round_robin"}."""
+    loads = []
+    for r in range(world_size):
+        idx = shard_by_cost(costs, r, world_size) if how == "lpt" else shard_indices(len(costs), r, world_size)
+        loads.append(sum(float(costs[i]) for i in idx))
+    mean = sum(loads) / world_size
+    return max(loads) / mean if mean > 0 else 1.0
+
+
 def _comm_device():
     if dist.is_initialized() and dist.get_backend() == "nccl":
         return torch.device("cuda", torch.cuda.current_device())

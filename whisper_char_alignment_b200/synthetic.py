@@ -45,7 +45,8 @@ def _sentence(rng, n_chars: int, min_words: int = 1) -> str:
     return " ".join(words)
 
 
-def make_utterance(rng, tokenizer, n_mels, seconds, n_chars, unit, fid, min_words=1, max_subwords=None) -> Utterance:
+def make_utterance(rng, tokenizer, n_mels, seconds, n_chars, unit, fid, min_words=1, max_subwords=None,
+                   with_mel=True) -> Utterance:
     n_samples = int(seconds * 16000)
     max_frames = min(n_samples // SAMPLES_PER_FRAME, MAX_FRAMES)
     text = _sentence(rng, n_chars, min_words)
@@ -56,10 +57,12 @@ def make_utterance(rng, tokenizer, n_mels, seconds, n_chars, unit, fid, min_word
     if len(text_tokens) > budget:
         text_tokens = text_tokens[:budget]
         text = tokenizer.decode(text_tokens)
-    mel = torch.zeros(n_mels, N_MEL_FRAMES)
-    n_mel = min(2 * max_frames, N_MEL_FRAMES)
-    noise = rng.standard_normal((n_mels, n_mel)).astype(np.float32) * 0.3
-    mel[:, :n_mel] = torch.from_numpy(noise)
+    mel = None  # with_mel=False: shape descriptors only (the caller creates the mel, e.g. directly in HBM)
+    if with_mel:
+        mel = torch.zeros(n_mels, N_MEL_FRAMES)
+        n_mel = min(2 * max_frames, N_MEL_FRAMES)
+        noise = rng.standard_normal((n_mels, n_mel)).astype(np.float32) * 0.3
+        mel[:, :n_mel] = torch.from_numpy(noise)
     tokens = torch.tensor([*tokenizer.sot_sequence, tokenizer.no_timestamps, *text_tokens, tokenizer.eot])
     return Utterance(fid, mel, n_samples, text, text_tokens, tokens, max_frames)
 
@@ -70,12 +73,12 @@ def timit_shaped(n, tokenizer, n_mels=80, seed=0):
             for i in range(n)]
 
 
-def librispeech_shaped(n, tokenizer, n_mels=80, seed=0):
+def librispeech_shaped(n, tokenizer, n_mels=80, seed=0, with_mel=True):
     rng = np.random.default_rng(seed)
     out = []
     for i in range(n):
         sec = rng.uniform(2.0, 30.0)
-        out.append(make_utterance(rng, tokenizer, n_mels, sec, int(sec * 13.5), "char", f"libri{i:04d}"))
+        out.append(make_utterance(rng, tokenizer, n_mels, sec, int(sec * 13.5), "char", f"libri{i:04d}", with_mel=with_mel))
     return out
 
 

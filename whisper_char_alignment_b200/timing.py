@@ -36,7 +36,7 @@ TOKENS_PER_SECOND = 50  # whisper.audio: SAMPLE_RATE // (HOP_LENGTH * 2)
 
 __all__ = [
     "get_attentions", "get_attentions_batch", "filter_attention", "force_align", "force_align_batch",
-    "dtw", "dtw_batch", "median_filter_softmax", "default_find_alignment",
+    "dtw", "dtw_batch", "median_filter_softmax", "default_find_alignment", "probe_heads_batch",
 ]
 
 
@@ -175,43 +175,45 @@ class _Plan:
     """Offsets of one batch inside the flat work buffers + the uploaded descriptors."""
 
     def __init__(self, ws_list, row_begin, n_sel_list, word_counts=None):
-        self.B = len(ws_list)
+        self.B = B = len(ws_list)
         self.device = ws_list[0].device
         self.base_ptr = ws_list[0].data_ptr()
-        recs = np.zeros(self.B, dtype=_cabi.UTT_DTYPE)
-        score_off = sel_off = matrix_off = path_off = jump_off = word_off = 0
-        self.n_heads = None
-        for b, w in enumerate(ws_list):
+        for w in ws_list:
             if w.device != self.device or w.dtype != torch.float32 or not w.is_contiguous():
                 raise _cabi.WcaError("attention maps must be contiguous fp32 CUDA tensors on one device")
-            heads = w.shape[0] * w.shape[1]
-            if self.n_heads is None:
-                self.n_heads = heads
-            elif heads != self.n_heads:
-                raise ValueError("all utterances of a batch must have the same number of heads")
-            T, F = int(w.shape[2]), int(w.shape[3])
-            delta = w.data_ptr() - self.base_ptr
-            assert delta % 4 == 0
-            r = recs[b]
-            r["n_tokens"], r["n_frames"] = T, F
-            r["row_begin"], r["row_end"] = row_begin, max(T - 1, row_begin)
-            r["n_sel"] = n_sel_list[b]
-            r["n_words"] = 0 if word_counts is None else word_counts[b]
-            r["ws_off"] = delta // 4
-            r["score_off"], r["sel_off"], r["matrix_off"] = score_off, sel_off, matrix_off
-            r["path_off"], r["jump_off"], r["word_off"] = path_off, jump_off, word_off
-            n_rows = int(r["row_end"] - r["row_begin"])
-            score_off += heads
-            sel_off += int(r["n_sel"])
-            matrix_off += n_rows * F
-            path_off += n_rows + F
-            jump_off += n_rows
-            word_off += int(r["n_words"]) + 1
+        shapes = np.array([w.shape for w in ws_list], dtype=np.int64).reshape(B, 4)
+        heads = shapes[:, 0] * shapes[:, 1]
+        if (heads != heads[0]).any():
+            raise ValueError("all utterances of a batch must have the same number of heads")
+        self.n_heads = int(heads[0])
+        T, F = shapes[:, 2], shapes[:, 3]
+        delta = np.array([w.data_ptr() for w in ws_list], dtype=np.int64) - self.base_ptr
+        assert (delta % 4 == 0).all()
+        n_sel = np.asarray(n_sel_list, dtype=np.int64)
+        n_words = np.zeros(B, dtype=np.int64) if word_counts is None else np.asarray(word_counts, dtype=np.int64)
+        row_end = np.maximum(T - 1, row_begin)
+        n_rows = row_end - row_begin
+
+        def starts(sizes):  # exclusive prefix sum
+            return np.concatenate([[0], np.cumsum(sizes)[:-1]]) if B else np.zeros(0, dtype=np.int64)
+
+        recs = np.zeros(B, dtype=_cabi.UTT_DTYPE)
+        recs["n_tokens"], recs["n_frames"] = T, F
+        recs["row_begin"], recs["row_end"] = row_begin, row_end
+        recs["n_sel"], recs["n_words"] = n_sel, n_words
+        recs["ws_off"] = delta // 4
+        recs["score_off"] = starts(heads)
+        recs["sel_off"] = starts(n_sel)
+        recs["matrix_off"] = starts(n_rows * F)
+        recs["path_off"] = starts(n_rows + F)
+        recs["jump_off"] = starts(n_rows)
+        recs["word_off"] = starts(n_words + 1)
         self.recs = recs
-        self.totals = dict(score=score_off, sel=sel_off, matrix=matrix_off, path=path_off, jump=jump_off, word=word_off)
-        self.max_tokens = int(recs["n_tokens"].max())
-        self.max_frames = int(recs["n_frames"].max())
-        self.max_rows = int((recs["row_end"] - recs["row_begin"]).max())
+        self.totals = dict(score=int(heads.sum()), sel=int(n_sel.sum()), matrix=int((n_rows * F).sum()),
+                           path=int((n_rows + F).sum()), jump=int(n_rows.sum()), word=int((n_words + 1).sum()))
+        self.max_tokens = int(T.max())
+        self.max_frames = int(F.max())
+        self.max_rows = int(n_rows.max())
         self.d_utts = _cabi.upload_utts(recs, self.device)
 
 
@@ -262,9 +264,11 @@ _SENTINEL = lambda: [[], [], [], [], None]  # noqa: E731  (what the reference re
 
 
 def force_align_batch(ws_list, tokens_list, tokenizer, aligned_unit_type="subword", aggregation="mean", topk=-1,
-                      w_colnorm=1.0, w_rownorm=1.0, w_coverage=0.0):
+                      w_colnorm=1.0, w_rownorm=1.0, w_coverage=0.0, *, return_matrix=True):
     """Batched force_align: one launch per stage for the whole list, one sync at the end.
-    Returns a list with, per utterance, what reference force_align returns."""
+    Returns a list with, per utterance, what reference force_align returns.  `return_matrix=False` leaves the
+    aggregated matrices on the device (the tuple carries None): the head sweep of probe_oracle.py reads only the
+    words and the end times of each of its 360 alignments per utterance."""
     B = len(ws_list)
     if B == 0:
         return []
@@ -276,11 +280,15 @@ def force_align_batch(ws_list, tokens_list, tokenizer, aligned_unit_type="subwor
     sot_len = len(tokenizer.sot_sequence)
 
     # host side: word grouping defines the boundaries the device gathers (timing.py:105-108)
-    words_all, wb_all = [], []
+    words_all, wb_all, seen = [], [], {}
     for toks in tokens_list:
-        words, word_tokens = split_tokens_on_spaces(list(toks) + [tokenizer.eot], tokenizer, aligned_unit_type)
-        words_all.append((words, word_tokens))
-        wb_all.append(np.pad(np.cumsum([len(t) for t in word_tokens[:-1]]), (1, 0)).astype(np.int32))
+        hit = seen.get(id(toks))  # the probe sweep passes the same list once per head
+        if hit is None:
+            words, word_tokens = split_tokens_on_spaces(list(toks) + [tokenizer.eot], tokenizer, aligned_unit_type)
+            hit = ((words, word_tokens), np.pad(np.cumsum([len(t) for t in word_tokens[:-1]]), (1, 0)).astype(np.int32))
+            seen[id(toks)] = hit
+        words_all.append(hit[0])
+        wb_all.append(hit[1])
     word_counts = [max(len(wt) - 1, 0) for _, wt in words_all]
 
     if aggregation == "grad_norm":
@@ -325,7 +333,7 @@ def force_align_batch(ws_list, tokens_list, tokenizer, aligned_unit_type="subwor
 
     # the only device->host traffic of the call: matrix (returned to the caller, as the
     # reference does at timing.py:102), W start/end times, k selected heads
-    matrix_h = matrix.cpu()
+    matrix_h = matrix.cpu() if return_matrix else None
     times_h = times.cpu().numpy()
     if sel_scores is not None:
         sel_h = sel.cpu().numpy()
@@ -345,7 +353,7 @@ def force_align_batch(ws_list, tokens_list, tokenizer, aligned_unit_type="subwor
             so, k = int(r["sel_off"]), int(r["n_sel"])
             scores = _score_table(sel_h[so: so + k], sel_scores_h[so: so + k], H[b])
         results.append((words, times_h[0, wo: wo + W].copy(), times_h[1, wo: wo + W].copy(),
-                        matrix_h[mo: mo + n_rows * F].view(n_rows, F), scores))
+                        matrix_h[mo: mo + n_rows * F].view(n_rows, F) if return_matrix else None, scores))
     return results
 
 
@@ -358,6 +366,41 @@ def force_align(ws, tokens, tokenizer, aligned_unit_type="subword", aggregation=
     when only EOT remains."""
     return force_align_batch([ws], [tokens], tokenizer, aligned_unit_type, aggregation, topk, w_colnorm, w_rownorm,
                              w_coverage)[0]
+
+
+def probe_heads_batch(ws_list, tokens_list, tokenizer, aligned_unit_type="subword", n_heads=360, w_colnorm=1.0,
+                      w_rownorm=1.0, w_coverage=0.0, *, return_matrix=False):
+    """The head sweep of reference probe_oracle.py:82-90 for a batch of utterances: rank the heads
+    (`filter_attention(w, topk=n_heads)`, :83), then align EVERY kept head on its own
+    (`force_align(w.unsqueeze(0), ..., aggregation="mean", topk=1)`, :89-90 -- with a single head the "mean" branch is
+    that head L2-normalised over tokens).  The reference does this with n_heads sequential force_align calls per
+    utterance; here all utterances' scores come from one launch and all B * n_heads single-head DTW problems from one
+    launch per stage.  Returns, per utterance, (outs, scores): scores as filter_attention returns them (ascending),
+    outs[i] what force_align returns for the head of scores[i]."""
+    B = len(ws_list)
+    if B == 0:
+        return []
+    ws_list = [w if w.is_contiguous() else w.contiguous() for w in ws_list]
+    total = [w.shape[0] * w.shape[1] for w in ws_list]
+    k = [min(int(n_heads), t) if n_heads > 0 else (t if n_heads == 0 else max(t + int(n_heads), 0)) for t in total]
+    plan = _Plan(ws_list, 0, k)
+    _, sel, sel_scores = _score_and_select(plan, w_colnorm, w_rownorm, w_coverage)
+    sel_h, score_h = sel.cpu().numpy(), sel_scores.cpu().numpy()
+    heads, toks, tables = [], [], []
+    for b, w in enumerate(ws_list):
+        so = int(plan.recs[b]["sel_off"])
+        table = _score_table(sel_h[so: so + k[b]], score_h[so: so + k[b]], w.shape[1])
+        tables.append(table)
+        flat = w.view(total[b], 1, 1, w.shape[2], w.shape[3])
+        heads.extend(flat[l * w.shape[1] + h] for _, (l, h), _ in table)
+        toks.extend([tokens_list[b]] * len(table))
+    outs = force_align_batch(heads, toks, tokenizer, aligned_unit_type, "mean", 1,
+                             return_matrix=return_matrix) if heads else []
+    res, pos = [], 0
+    for b in range(B):
+        res.append((outs[pos: pos + len(tables[b])], tables[b]))
+        pos += len(tables[b])
+    return res
 
 
 def default_find_alignment(model, tokenizer, text_tokens, mel, max_frames, *, medfilt_width=7, qk_scale=1.0):

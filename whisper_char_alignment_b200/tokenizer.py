@@ -21,14 +21,19 @@ CJK_LIKE = frozenset({"zh", "ja", "th", "lo", "my", "yue"})
 
 
 class ByteTokenizer:
-    def __init__(self, multilingual: bool = True, language: str = "en", task: str = "transcribe"):
+    def __init__(self, multilingual: bool = True, language: str = "en", task: str = "transcribe", num_languages: int = 99):
         self.multilingual = multilingual
         self.language = language
         self.task = task
+        self.num_languages = num_languages
         if multilingual:
+            # <|endoftext|> <|sot|> [num_languages language tokens] <|translate|> <|transcribe|> <|startoflm|>
+            # <|startofprev|> <|nospeech|> <|notimestamps|> <|0.00|> ...: the ids after the language block move with
+            # its size (99 languages up to large-v2 -> notimestamps 50363; 100 for large-v3 -> 50364)
+            extra = num_languages - 99
             self.eot, self.sot = 50257, 50258
-            self.no_timestamps, self.timestamp_begin = 50363, 50364
-            self.sot_sequence = (self.sot, 50259, 50359)  # <|sot|><|en|><|transcribe|>
+            self.no_timestamps, self.timestamp_begin = 50363 + extra, 50364 + extra
+            self.sot_sequence = (self.sot, 50259, 50359 + extra)  # <|sot|><|en|><|transcribe|>
         else:
             self.eot, self.sot = 50256, 50257
             self.no_timestamps, self.timestamp_begin = 50362, 50363
@@ -126,4 +131,4 @@ def get_tokenizer(multilingual: bool = True, *, language: str | None = None, tas
                   num_languages: int = 99) -> ByteTokenizer:
     lang = (language or "en").lower()
     lang = {"english": "en"}.get(lang, lang)
-    return ByteTokenizer(multilingual, lang, task or "transcribe")
+    return ByteTokenizer(multilingual, lang, task or "transcribe", num_languages if multilingual else 0)

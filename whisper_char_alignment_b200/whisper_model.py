@@ -259,17 +259,38 @@ class Whisper(nn.Module):
         return self.dims.n_vocab - 51765 - int(self.is_multilingual)
 
 
-def load_model(name_or_path: str, device=None, *, seed: int = 0, qk_gain: float = 1.0) -> Whisper:
-    """A checkpoint file ({"dims", "model_state_dict"}) if `name_or_path` is a path, else a
-    seeded random-init model of the named size (no checkpoints are reachable offline)."""
-    import os
+#: tiny dims for smoke runs: 30 s context and head width 64 like the published models
+TEST_SIZES = {
+    "micro": (80, 1500, 128, 2, 2, 51865, 448, 128, 2, 2),
+    "mini": (80, 1500, 256, 4, 2, 51865, 448, 256, 4, 3),
+}
 
+
+def load_model(name_or_path: str, device=None, *, seed: int = 0, qk_gain: float = 1.0) -> Whisper:
+    """A checkpoint file ({"dims", "model_state_dict"}, the published openai-whisper format) if `name_or_path` is a
+    path; `random:<size>` (e.g. `random:medium`, `random:micro`) for a SEEDED RANDOM-INIT model of that size.  A bare
+    size name is refused: no checkpoint can be downloaded offline, and aligning with random weights must be asked for
+    explicitly -- the results look like a real run but mean nothing.  The returned model carries `.model_source`."""
     if os.path.isfile(name_or_path):
         ckpt = torch.load(name_or_path, map_location="cpu", weights_only=True)
         model = Whisper(ModelDimensions(**ckpt["dims"]))
         model.load_state_dict(ckpt["model_state_dict"])
+        model.model_source = f"checkpoint:{os.path.abspath(name_or_path)}"
+    elif name_or_path.startswith("random:"):
+        size = name_or_path.split(":", 1)[1]
+        if size in TEST_SIZES:
+            dims = ModelDimensions(*TEST_SIZES[size])
+        elif size in SIZES:
+            dims = dims_for(size)
+        else:
+            raise ValueError(f"unknown model size {size!r}: one of {sorted(SIZES) + sorted(TEST_SIZES)}")
+        model = random_init(dims, seed=seed, qk_gain=qk_gain)
+        model.model_source = f"random-init:{size}:seed{seed}:qk_gain{qk_gain:g}"
     else:
-        model = random_init(dims_for(name_or_path), seed=seed, qk_gain=qk_gain)
+        raise FileNotFoundError(
+            f"{name_or_path!r} is not a checkpoint file, and openai-whisper (which would download it) is not installed. "
+            f"Pass a checkpoint path, or `random:{name_or_path}` to align with a seeded RANDOM-INIT model "
+            "(synthetic benchmarks / smoke runs only: its alignments are meaningless).")
     model.eval()
     return model if device is None else model.to(device)
 
