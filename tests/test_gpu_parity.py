@@ -15,10 +15,11 @@ pytestmark = pytest.mark.gpu
 MAP_RTOL = 1e-4  # north_star: attention maps within 1e-4 relative in fp32 (kernel given identical Q/K)
 # End to end (cuBLAS forward + every kernel) against the reference's CPU fp32 result.  The forward's GEMMs sum in
 # another order than the CPU's, which moves the logits by a few fp32 ulps of their magnitude and the maps by the
-# same RELATIVE amount.  Stated tolerances, with the measured maxima printed by every run (MEASURE[...] lines):
-#   native   (cuBLAS SIMT SGEMM, what the reference's GPU path would use)   north_star's 1e-4
-#   bf16x9   (cuBLAS 12.9 BF16x9-emulated fp32 GEMMs, the benchmarked mode)  the stated tolerance of that mode
-E2E_RTOL = {"native": 1e-3, "bf16x9": 1e-3}[GEMM_MODE]
+# same RELATIVE amount.  The bound is north_star's 1e-4 in BOTH fp32-GEMM modes; the measured maxima are printed by
+# every run (MEASURE[...] lines).  Measured on a B200 (round 2, all fixtures + medium/large-v3 at full length):
+#   native   (cuBLAS SIMT SGEMM)                                              maps <= 5.0e-5, matrices <= 3.3e-5
+#   bf16x9   (cuBLAS 12.9 BF16x9-emulated fp32 GEMMs, the benchmarked mode)   maps <= 3.6e-5, matrices <= 3.1e-5
+E2E_RTOL = {"native": 1e-4, "bf16x9": 1e-4}[GEMM_MODE]
 
 
 def assert_same_ranking(got, want, rtol):
@@ -319,8 +320,8 @@ def test_probe_style_single_head_alignment(timing, tokenizer, dev):
 @pytest.mark.parametrize("name", NAMES)
 def test_end_to_end_against_reference_fixture(name, timing, tokenizer, oracle_models, dev):
     """Model forward on cuBLAS + every kernel, against what the reference produced on CPU.
-    fp32 GEMMs in another summation order move the maps by ~1e-5 relative; the stated bound
-    for the whole network is 1e-3 (the kernel-only bound is MAP_RTOL, tested above)."""
+    fp32 GEMMs in another summation order move the maps by a few 1e-5 relative (measured and printed);
+    the bound for the whole network is north_star's 1e-4, like the kernel-only bound MAP_RTOL."""
     g = load_golden(name)
     c = g["case"]
     model = product_model(oracle_models(c["model"], c.get("seed", 0), c.get("gain", 4.0)), dev)
@@ -625,8 +626,8 @@ def test_probe_sweep_at_medium_size_every_head_bit_exact(timing, tokenizer, dev)
 def test_medium_model_end_to_end_against_the_cpu_oracle(timing, tokenizer, oracle_models, dev):
     """BASELINE.json's named architecture (Whisper-medium dims, seeded random init, cross-attention gain 4) on
     TIMIT-shaped synthetic utterances: the whole B200 path (cuBLAS forward, tcgen05 attention and capture, scoring,
-    aggregation, DTW) against the CPU restatement of the reference on the same weights and inputs.  Maps within 1e-3,
-    the same top-10 heads, word boundaries equal to the frame."""
+    aggregation, DTW) against the CPU restatement of the reference on the same weights and inputs.  Maps within 1e-4,
+    the same top-10 heads in the same order, word boundaries equal to the frame."""
     from oracle import ref_path
     from whisper_char_alignment_b200 import synthetic
 

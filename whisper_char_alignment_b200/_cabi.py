@@ -193,20 +193,42 @@ def upload_utts(records: np.ndarray, device) -> torch.Tensor:
 # ---------------------------------------------------------------------------------
 # thin wrappers: tensors in, status checked, nothing else
 # ---------------------------------------------------------------------------------
+def _rows_and_pitch(t: torch.Tensor, name: str):
+    """(rows, floats between rows) of an fp32 (..., rows, width) tensor whose rows are evenly strided -- a contiguous
+    tensor or a column slice of a wider one (e.g. one layer's K inside the all-layer K/V projection)."""
+    if not t.is_cuda:
+        raise WcaError(f"{name} must live on a CUDA device (no CPU fallback exists)")
+    if t.dtype != torch.float32 or t.dim() < 2 or t.stride(-1) != 1:
+        raise WcaError(f"{name} must be fp32 with unit stride along the width")
+    pitch = t.stride(-2)
+    rows = t.shape[-2]
+    for dim in range(t.dim() - 3, -1, -1):  # leading dims must continue the same row pitch
+        if t.shape[dim] != 1 and t.stride(dim) != rows * pitch:
+            raise WcaError(f"{name}: rows are not evenly strided")
+        rows *= t.shape[dim]
+    return rows, pitch
+
+
 def capture_attention(q_layers: Sequence[torch.Tensor], k_layers: Sequence[torch.Tensor], n_heads: int,
-                      ld_q: int, ld_k: int, d_utts: torch.Tensor, n_utts: int, max_tokens: int, max_frames: int,
-                      medfilt_width: int, qk_scale: float, ws: torch.Tensor, flags: int = 0):
+                      ld_q: int | None, ld_k: int | None, d_utts: torch.Tensor, n_utts: int, max_tokens: int, max_frames: int,
+                      medfilt_width: int, qk_scale: float, ws: torch.Tensor, flags: int = 0, partials: torch.Tensor | None = None):
+    """q_layers / k_layers: per decoder layer, (..., rows, n_heads*64) fp32 with evenly strided rows (ld_q / ld_k are
+    taken from the tensors when None)."""
     n_layers = len(q_layers)
     if n_layers != len(k_layers) or not 1 <= n_layers <= WCA_MAX_LAYERS:
         raise WcaError(f"bad layer count {n_layers}")
-    qp = (ctypes.c_void_p * n_layers)(*[_dev_ptr(t, torch.float32, "Q") for t in q_layers])
-    kp = (ctypes.c_void_p * n_layers)(*[_dev_ptr(t, torch.float32, "K") for t in k_layers])
     head_dim = 64
-    q_rows = q_layers[0].numel() // ld_q
-    k_rows = k_layers[0].numel() // ld_k
+    q_rows, q_pitch = _rows_and_pitch(q_layers[0], "Q")
+    k_rows, k_pitch = _rows_and_pitch(k_layers[0], "K")
+    ld_q = q_pitch if ld_q is None else ld_q
+    ld_k = k_pitch if ld_k is None else ld_k
     for q, k in zip(q_layers, k_layers):
-        if q.numel() != q_rows * ld_q or k.numel() != k_rows * ld_k:
-            raise WcaError("every layer's Q (and K) must have the same shape")
+        if _rows_and_pitch(q, "Q") != (q_rows, q_pitch) or _rows_and_pitch(k, "K") != (k_rows, k_pitch):
+            raise WcaError("every layer's Q (and K) must have the same shape and row pitch")
+    if q_pitch != ld_q or k_pitch != ld_k:
+        raise WcaError("ld_q / ld_k disagree with the tensors' row pitch")
+    qp = (ctypes.c_void_p * n_layers)(*[t.data_ptr() for t in q_layers])
+    kp = (ctypes.c_void_p * n_layers)(*[t.data_ptr() for t in k_layers])
     with _timed("wca_capture_attention"):
         _check(
             load().wca_capture_attention(qp, kp, n_layers, n_heads, head_dim, ld_q, ld_k, q_rows, k_rows,

@@ -78,9 +78,13 @@ def _cluster_bucket(n_frames: int) -> int:
 
 
 def _as_f32_rows(t: torch.Tensor) -> torch.Tensor:
+    """fp32 rows with unit stride along the width; evenly strided rows are kept as they are (the product model hands
+    over column slices of its fused projections), anything else is made contiguous."""
     t = t.detach()
     if t.dtype != torch.float32:
         t = t.float()
+    if t.stride(-1) == 1 and all(t.shape[d] == 1 or t.stride(d) == t.stride(d + 1) * t.shape[d + 1] for d in range(t.dim() - 2)):
+        return t
     return t.contiguous()
 
 
@@ -113,11 +117,17 @@ def get_attentions_batch(mels, tokens_list: Sequence[torch.Tensor], model, token
         for t in tokens_list
     ])
 
-    with torch.no_grad(), _CrossAttentionTap(model) as tap:
-        out_logits = model(mels, tok)
-    q_layers = [_as_f32_rows(q) for q in tap.q]
-    k_layers = [_as_f32_rows(k) for k in tap.k]
-    width = q_layers[0].shape[-1]
+    if hasattr(model, "forward_with_cross_qk"):
+        # the product model hands the projections over itself (its cross-attention K of all layers comes from ONE GEMM,
+        # so there is no per-layer `key` module call to hook)
+        with torch.no_grad():
+            out_logits, qs, ks = model.forward_with_cross_qk(mels, tok)
+    else:
+        with torch.no_grad(), _CrossAttentionTap(model) as tap:
+            out_logits = model(mels, tok)
+        qs, ks = tap.q, tap.k
+    q_layers = [_as_f32_rows(q) for q in qs]
+    k_layers = [_as_f32_rows(k) for k in ks]
 
     recs = np.zeros(B, dtype=_cabi.UTT_DTYPE)
     off = 0
@@ -137,7 +147,7 @@ def get_attentions_batch(mels, tokens_list: Sequence[torch.Tensor], model, token
     for _, members in sorted(buckets.items()):
         sub = recs[members]
         d_utts = _cabi.upload_utts(sub, device)
-        _cabi.capture_attention(q_layers, k_layers, n_heads, width, width, d_utts, len(members),
+        _cabi.capture_attention(q_layers, k_layers, n_heads, None, None, d_utts, len(members),
                                 int(sub["n_tokens"].max()), int(sub["n_frames"].max()), int(medfilt_width),
                                 float(qk_scale), ws, flags)
     weights, logits = [], []

@@ -76,6 +76,33 @@ class _Conv(nn.Conv1d):
         return super()._conv_forward(x, weight.to(x.dtype), None if bias is None else bias.to(x.dtype))
 
 
+#: True: projections that read the same activations run as ONE cuBLAS GEMM against concatenated weights -- Q/K/V of a
+#: self-attention (N = 3d) and the cross-attention K and V of ALL decoder layers (N = 2 * layers * d of the encoder
+#: output).  Same products, fewer launches: with BF16x9 emulation every GEMM first scans its operands for Inf/NaN, and
+#: `xa` (batch * 1500 rows) was scanned 2 * layers times.  False: one GEMM per nn.Linear, as the module tree suggests.
+FUSED_PROJECTIONS = os.environ.get("WCA_FUSED_PROJECTIONS", "1") != "0"
+
+
+class _FusedWeights:
+    """Concatenation of several projections' weights (and biases, zeros where a projection has none), rebuilt when
+    any parameter is reassigned, modified in place or moved."""
+
+    def __init__(self):
+        self.key = None
+        self.weight = self.bias = None
+
+    def get(self, projections, dtype):
+        key = tuple((p.weight.data_ptr(), p.weight._version, None if p.bias is None else p.bias._version)
+                    for p in projections) + (dtype,)
+        if key != self.key:
+            with torch.no_grad():
+                self.weight = torch.cat([p.weight.detach().to(dtype) for p in projections], dim=0)
+                self.bias = torch.cat([torch.zeros(p.weight.shape[0], dtype=dtype, device=p.weight.device)
+                                       if p.bias is None else p.bias.detach().to(dtype) for p in projections])
+            self.key = key
+        return self.weight, self.bias
+
+
 class Attention(nn.Module):
     """query/key/value/out projections (key without bias) around SDPA."""
 
@@ -86,14 +113,28 @@ class Attention(nn.Module):
         self.key = _Proj(width, width, bias=False)
         self.value = _Proj(width, width)
         self.out = _Proj(width, width)
+        self._qkv = _FusedWeights()
 
     def _split(self, t):
         b, n, _ = t.shape
         return t.view(b, n, self.n_head, -1).transpose(1, 2)
 
-    def forward(self, x, xa=None, causal: bool = False):
-        src = x if xa is None else xa
-        q, k, v = self.query(x), self.key(src), self.value(src)
+    def forward(self, x, xa=None, causal: bool = False, kv=None, tap=None):
+        """kv: (k, v) already projected (views into the decoder's all-layer K/V GEMM); tap: list that receives
+        (q, k) of a cross-attention for the capture kernel."""
+        fused = FUSED_PROJECTIONS and x.is_cuda and not torch.is_grad_enabled()
+        if kv is not None:
+            q, (k, v) = self.query(x), kv
+        elif xa is None and fused:
+            w, b = self._qkv.get((self.query, self.key, self.value), x.dtype)
+            d = x.shape[-1]
+            qkv = F.linear(x, w, b)  # (batch, n, 3d): q, k, v are strided views, read in place by the kernels
+            q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+        else:
+            src = x if xa is None else xa
+            q, k, v = self.query(x), self.key(src), self.value(src)
+        if tap is not None:
+            tap.append((q, k))
         if (not causal and ENCODER_ATTENTION == "wca" and q.is_cuda and q.dtype == torch.float32
                 and q.shape[-1] == 64 * self.n_head):
             # unmasked attention (encoder self-attention, decoder cross-attention output): the sm_100a
@@ -102,6 +143,8 @@ class Attention(nn.Module):
             from . import _cabi
 
             return self.out(_cabi.full_attention(q, k, v, self.n_head)), None
+        if not q.is_contiguous():  # views of a fused projection: head split needs the plain (batch, n, d) layout
+            q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         q, k, v = self._split(q), self._split(k), self._split(v)
         # SDPA's default scale is d_head^-1/2 == (d_head^-1/4)^2, the published scaling
         ctx = F.scaled_dot_product_attention(q, k, v, is_causal=causal and q.shape[2] > 1)
@@ -136,7 +179,7 @@ class Block(nn.Module):
         self.mlp = nn.Sequential(_Proj(width, 4 * width), nn.GELU(), _Proj(4 * width, width))
         self.mlp_ln = _Norm(width)
 
-    def forward(self, x, xa=None, causal: bool = False, pending=None):
+    def forward(self, x, xa=None, causal: bool = False, pending=None, kv=None, tap=None):
         """Upstream: x += attn(ln(x)); x += cross_attn(ln(x), xa); x += mlp(ln(x)).  Every residual add is
         paired with the LayerNorm that follows it, so the last add of a block is handed to the next one
         (`pending`): returns (x, h) with the block's output being x + h."""
@@ -144,7 +187,7 @@ class Block(nn.Module):
         h = self.attn(n, causal=causal)[0]
         if self.cross_attn is not None:
             x, n = _add_ln(x, h, self.cross_attn_ln)
-            h = self.cross_attn(n, xa)[0]
+            h = self.cross_attn(n, xa, kv=kv, tap=tap)[0]
         x, n = _add_ln(x, h, self.mlp_ln)
         return x, self.mlp(n)
 
@@ -199,13 +242,27 @@ class TextDecoder(nn.Module):
         self.positional_embedding = nn.Parameter(torch.empty(n_ctx, width))
         self.blocks = nn.ModuleList([Block(width, heads, cross=True) for _ in range(layers)])
         self.ln = _Norm(width)
+        self._cross_kv = _FusedWeights()
 
-    def forward(self, tokens, xa):
+    def cross_kv_all_layers(self, xa):
+        """K and V of every layer's cross-attention in ONE GEMM over the encoder output: (batch, n_ctx, 2 * layers * d),
+        layer l's K at columns [2l d, (2l+1) d), its V right after.  The kernels read the strided views in place."""
+        projections = [p for blk in self.blocks for p in (blk.cross_attn.key, blk.cross_attn.value)]
+        w, b = self._cross_kv.get(projections, xa.dtype)
+        return F.linear(xa, w, b)
+
+    def forward(self, tokens, xa, tap=None):
+        """tap: list that receives (q, k) of every layer's cross-attention (what timing.get_attentions captures)."""
         x = self.token_embedding(tokens) + self.positional_embedding[: tokens.shape[-1]]
         x = x.to(xa.dtype)
+        d = x.shape[-1]
+        kv_all = None
+        if FUSED_PROJECTIONS and xa.is_cuda and not torch.is_grad_enabled():
+            kv_all = self.cross_kv_all_layers(xa)
         pending = None
-        for blk in self.blocks:
-            x, pending = blk(x, xa, causal=True, pending=pending)
+        for l, blk in enumerate(self.blocks):
+            kv = None if kv_all is None else (kv_all[..., 2 * l * d:(2 * l + 1) * d], kv_all[..., (2 * l + 1) * d:(2 * l + 2) * d])
+            x, pending = blk(x, xa, causal=True, pending=pending, kv=kv, tap=tap)
         x = _add_ln(x, pending, self.ln)[1]
         return self._vocab_logits(x)
 
@@ -245,6 +302,15 @@ class Whisper(nn.Module):
 
     def forward(self, mel, tokens):
         return self.decoder(tokens, self.encoder(mel))
+
+    def forward_with_cross_qk(self, mel, tokens):
+        """(logits, [q_l (batch, T, d)], [k_l (batch, n_ctx, d)]): the teacher-forced forward plus the cross-attention
+        projections of every decoder layer, as the capture kernel reads them (k_l may be a strided view of the all-layer
+        K/V GEMM).  timing.get_attentions uses this when the model offers it; any other module tree (a stock
+        openai-whisper model) is tapped with forward hooks on cross_attn.query / cross_attn.key instead."""
+        tap = []
+        logits = self.decoder(tokens, self.encoder(mel), tap=tap)
+        return logits, [q for q, _ in tap], [k for _, k in tap]
 
     @property
     def device(self):
