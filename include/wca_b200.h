@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define WCA_ABI_VERSION 3
+#define WCA_ABI_VERSION 4
 #define WCA_MAX_LAYERS 32      /* decoder layers of the largest published Whisper (large-v3) */
 #define WCA_MAX_MEDFILT 31     /* odd widths 1..31 */
 #define WCA_TOKENS_PER_SECOND 50.0 /* whisper.audio.TOKENS_PER_SECOND, timing.py:10,111 */
@@ -66,6 +66,7 @@ typedef struct wca_utt {
     int64_t path_off;   /* int32 offset of the path buffers, capacity N+F each                            */
     int64_t jump_off;   /* int32 offset of the N jump frames                                              */
     int64_t word_off;   /* offset of word_boundaries (W+1 int32) and of start/end times (W float64)       */
+    int64_t part_off;   /* float offset of the head-score partials (wca_capture_attention d_partials)      */
 } wca_utt_t;
 
 WCA_API int wca_abi_version(void);
@@ -85,15 +86,23 @@ WCA_API int wca_device_info(int *sm_count, int *compute_capability);
  * matrix of q_rows rows with leading dimension ld_q floats whose row (q_row0 + t) holds
  * token t, columns [h*Dh, (h+1)*Dh) belong to head h; likewise K with k_rows, ld_k and
  * frame rows (the row counts bound the TMA tensor maps: rows past them read as zero).
- * Output: d_ws + ws_off, layout (L, H, T, F) fp32, exactly what get_attentions returns. */
+ * Output: d_ws + ws_off, layout (L, H, T, F) fp32, exactly what get_attentions returns.
+ * d_partials (may be NULL): head-score partials for wca_head_scores_from_partials, so that scoring the heads
+ * (timing.py:17-34) does not read the maps a second time.  Per utterance, at d_partials + part_off, with
+ * B = ceil(T / 128) token blocks: [L*H][B] floats sum_t ||p[t,:]||_2 over the rows of the block, then
+ * [L*H][B][F] floats sum_t p[t,f]^2 over the rows of the block (wca_capture_partials_floats floats in all).
+ * Only the tcgen05 kernel writes them: wca_capture_writes_partials tells for a launch geometry; passing a
+ * non-NULL d_partials when it answers 0 is an error. */
 #define WCA_CAPTURE_RAW_LOGITS 1u
 #define WCA_CAPTURE_FORCE_SIMT 2u /* use the CUDA-core kernel instead of tcgen05 (test cross-check) */
 #define WCA_CAPTURE_TRACE 4u      /* debug: CTA 0 records a clock64 timeline, see wca_debug_capture_trace */
 WCA_API int wca_capture_attention(const float *const *h_q_layers, const float *const *h_k_layers, int n_layers,
                           int n_heads_per_layer, int head_dim, int64_t ld_q, int64_t ld_k,
                           int64_t q_rows, int64_t k_rows, const wca_utt_t *d_utts, int n_utts, int max_tokens, int max_frames,
-                          int medfilt_width, float qk_scale, float *d_ws, unsigned flags,
+                          int medfilt_width, float qk_scale, float *d_ws, float *d_partials, unsigned flags,
                           wca_stream_t stream);
+WCA_API int wca_capture_writes_partials(int max_frames, int medfilt_width, unsigned flags);
+WCA_API int64_t wca_capture_partials_floats(int n_heads, int n_tokens, int n_frames);
 
 /* Debug only: copies the timeline recorded by the last WCA_CAPTURE_TRACE launch (synchronises
  * the device).  Returns the number of int64 entries written (tiles x events) or a status < 0. */
@@ -142,6 +151,11 @@ WCA_API int wca_medfilt_softmax(const float *d_in, int64_t n_rows, int64_t ld_in
 WCA_API int wca_head_scores(const float *d_ws, const wca_utt_t *d_utts, int n_utts, int n_heads, int max_tokens,
                     int max_frames, float w_colnorm, float w_rownorm, float w_coverage, float *d_scores,
                     wca_stream_t stream);
+
+/* (3a') The same scores from the partials of wca_capture_attention (no coverage term: callers with
+ * w_coverage > 0 use wca_head_scores).  n_heads = L*H. */
+WCA_API int wca_head_scores_from_partials(const float *d_partials, const wca_utt_t *d_utts, int n_utts, int n_heads,
+                                  float w_colnorm, float w_rownorm, float *d_scores, wca_stream_t stream);
 
 /* (3b) Top-k head selection.  Replaces timing.py:36 `sorted(scores)[-topk:]`: ascending
  * by (score, layer, head); the last min(topk, n_heads) survive, still ascending.  Writes

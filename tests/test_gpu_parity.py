@@ -544,6 +544,11 @@ def test_capture_at_baseline_shapes_vs_torch_fp32(cfg, dev):
         recs[b]["q_row0"], recs[b]["k_row0"], recs[b]["ws_off"] = b * t_max, b * 1500, off
         off += L * H * t_list[b] * f_list[b]
     outs = {}
+    part_off = 0
+    for b in range(B):  # head-score partials of the tcgen05 launch (one block per utterance)
+        recs[b]["part_off"], recs[b]["score_off"] = part_off, b * L * H
+        part_off += _cabi.capture_partials_floats(L * H, t_list[b], f_list[b])
+    partials = torch.full((part_off,), float("nan"), device=dev)
     for name, flags in (("tc", 0), ("simt", _cabi.WCA_CAPTURE_FORCE_SIMT)):
         ws = torch.zeros(off, device=dev)
         buckets = {}
@@ -551,9 +556,21 @@ def test_capture_at_baseline_shapes_vs_torch_fp32(cfg, dev):
             buckets.setdefault(1 if flags else _cluster_bucket(f_list[b]), []).append(b)
         for _, members in sorted(buckets.items()):
             sub = recs[members]
+            assert _cabi.capture_writes_partials(int(sub["n_frames"].max()), W, flags) == (name == "tc")
             _cabi.capture_attention(q, k, H, width, width, _cabi.upload_utts(sub, dev), len(members),
-                                    int(sub["n_tokens"].max()), int(sub["n_frames"].max()), W, 1.0, ws, flags)
+                                    int(sub["n_tokens"].max()), int(sub["n_frames"].max()), W, 1.0, ws, flags,
+                                    partials if name == "tc" else None)
         outs[name] = ws
+    # scores finished from the partials == scores computed by reading the maps (every partial slot was written: no NaN left)
+    assert not torch.isnan(partials).any()
+    d_all = _cabi.upload_utts(recs, dev)
+    for w_col, w_row in ((1.0, 1.0), (0.5, 2.0), (0.0, 1.0)):
+        s_read = torch.empty(B * L * H, device=dev)
+        s_part = torch.empty(B * L * H, device=dev)
+        _cabi.head_scores(outs["tc"].data_ptr(), d_all, B, L * H, t_max, max(f_list), w_col, w_row, 0.0, s_read)
+        _cabi.head_scores_from_partials(partials, d_all, B, L * H, w_col, w_row, s_part)
+        record_measure("scores_from_partials_vs_reading_the_maps_max_rel_err", max_rel_err(s_part.cpu().numpy(), s_read.cpu().numpy(), atol=0, rtol=1))
+        torch.testing.assert_close(s_part, s_read, rtol=1e-5, atol=0)
     for b in range(B):
         T, F = t_list[b], f_list[b]
         n = L * H * T * F

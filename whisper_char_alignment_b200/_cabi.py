@@ -20,11 +20,11 @@ WCA_CAPTURE_RAW_LOGITS = 1
 WCA_CAPTURE_FORCE_SIMT = 2
 WCA_CAPTURE_TRACE = 4
 WCA_MAX_LAYERS = 32
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 EXPORTS = (
     "wca_abi_version", "wca_last_error", "wca_launch_count", "wca_device_info", "wca_capture_attention", "wca_full_attention", "wca_add_layernorm", "wca_debug_enc_attn_buffer", "wca_debug_capture_trace", "wca_medfilt_softmax",
-    "wca_head_scores", "wca_topk_heads", "wca_aggregate_heads", "wca_dtw_workspace_bytes", "wca_dtw_align",
+    "wca_head_scores", "wca_head_scores_from_partials", "wca_capture_writes_partials", "wca_capture_partials_floats", "wca_topk_heads", "wca_aggregate_heads", "wca_dtw_workspace_bytes", "wca_dtw_align",
 )
 
 
@@ -41,13 +41,14 @@ class UttDesc(ctypes.Structure):
         ("q_row0", ctypes.c_int64), ("k_row0", ctypes.c_int64), ("ws_off", ctypes.c_int64),
         ("score_off", ctypes.c_int64), ("sel_off", ctypes.c_int64), ("matrix_off", ctypes.c_int64),
         ("path_off", ctypes.c_int64), ("jump_off", ctypes.c_int64), ("word_off", ctypes.c_int64),
+        ("part_off", ctypes.c_int64),
     ]
 
 
 UTT_DTYPE = np.dtype(
     [(name, np.int32 if ct is ctypes.c_int32 else np.int64) for name, ct in UttDesc._fields_], align=True
 )
-assert UTT_DTYPE.itemsize == ctypes.sizeof(UttDesc) == 96
+assert UTT_DTYPE.itemsize == ctypes.sizeof(UttDesc) == 104
 
 _lib = None
 
@@ -71,8 +72,12 @@ def load() -> ctypes.CDLL:
     lib.wca_last_error.restype = ctypes.c_char_p
     lib.wca_launch_count.restype = ctypes.c_uint64
     lib.wca_device_info.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(i32)]
-    lib.wca_capture_attention.argtypes = [vp, vp, i32, i32, i32, i64, i64, i64, i64, vp, i32, i32, i32, i32, f32, vp,
+    lib.wca_capture_attention.argtypes = [vp, vp, i32, i32, i32, i64, i64, i64, i64, vp, i32, i32, i32, i32, f32, vp, vp,
                                           ctypes.c_uint, vp]
+    lib.wca_capture_writes_partials.argtypes = [i32, i32, ctypes.c_uint]
+    lib.wca_capture_partials_floats.restype = i64
+    lib.wca_capture_partials_floats.argtypes = [i32, i32, i32]
+    lib.wca_head_scores_from_partials.argtypes = [vp, vp, i32, i32, f32, f32, vp, vp]
     lib.wca_full_attention.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, vp]
     lib.wca_add_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, f32, vp]
     lib.wca_medfilt_softmax.argtypes = [vp, i64, i64, i32, i32, f32, vp, vp]
@@ -234,8 +239,27 @@ def capture_attention(q_layers: Sequence[torch.Tensor], k_layers: Sequence[torch
             load().wca_capture_attention(qp, kp, n_layers, n_heads, head_dim, ld_q, ld_k, q_rows, k_rows,
                                          _dev_ptr(d_utts), n_utts,
                                          max_tokens, max_frames, medfilt_width, float(qk_scale),
-                                         _dev_ptr(ws, torch.float32, "ws"), flags, _stream()),
+                                         _dev_ptr(ws, torch.float32, "ws"), _dev_ptr(partials, torch.float32, "partials"),
+                                         flags, _stream()),
             "wca_capture_attention",
+        )
+
+
+def capture_writes_partials(max_frames: int, medfilt_width: int, flags: int = 0) -> bool:
+    return bool(load().wca_capture_writes_partials(int(max_frames), int(medfilt_width), int(flags)))
+
+
+def capture_partials_floats(n_heads: int, n_tokens: int, n_frames: int) -> int:
+    return int(load().wca_capture_partials_floats(int(n_heads), int(n_tokens), int(n_frames)))
+
+
+def head_scores_from_partials(partials: torch.Tensor, d_utts, n_utts, n_heads, w_col, w_row, scores):
+    with _timed("wca_head_scores_from_partials"):
+        _check(
+            load().wca_head_scores_from_partials(_dev_ptr(partials, torch.float32, "partials"), _dev_ptr(d_utts), n_utts,
+                                                 n_heads, float(w_col), float(w_row),
+                                                 _dev_ptr(scores, torch.float32, "scores"), _stream()),
+            "wca_head_scores_from_partials",
         )
 
 

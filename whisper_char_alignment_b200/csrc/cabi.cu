@@ -41,7 +41,8 @@ static int device_sm_count(int *sms, int *cc) {
 int launch_capture_logits_simt(const float *const *, const float *const *, int, int, int64_t, int64_t,
                                const wca_utt_t *, int, int, float *, cudaStream_t);
 int launch_capture_tc(const float *const *, const float *const *, int, int, int64_t, int64_t, int64_t, int64_t,
-                      const wca_utt_t *, int, int, int, int, float, float *, unsigned, int, cudaStream_t);
+                      const wca_utt_t *, int, int, int, int, float, float *, float *, unsigned, int, cudaStream_t);
+int launch_scores_from_partials(const float *, const wca_utt_t *, int, int, float, float, float *, cudaStream_t);
 bool capture_tc_supported(int max_tokens, int max_frames, int medfilt_width);
 int read_capture_trace(long long *, int);
 int launch_medfilt_softmax_rows(const float *, int64_t, int64_t, int, int, float, float *, int, cudaStream_t);
@@ -79,7 +80,7 @@ int wca_device_info(int *sm_count, int *compute_capability) { return device_sm_c
 int wca_capture_attention(const float *const *h_q_layers, const float *const *h_k_layers, int n_layers,
                           int n_heads_per_layer, int head_dim, int64_t ld_q, int64_t ld_k, int64_t q_rows,
                           int64_t k_rows, const wca_utt_t *d_utts, int n_utts, int max_tokens, int max_frames, int medfilt_width, float qk_scale, float *d_ws,
-                          unsigned flags, wca_stream_t stream) {
+                          float *d_partials, unsigned flags, wca_stream_t stream) {
     WCA_CHECK_ARG(h_q_layers && h_k_layers && d_utts && d_ws, "wca_capture_attention: null pointer");
     WCA_CHECK_ARG(n_layers >= 1 && n_layers <= WCA_MAX_LAYERS, "wca_capture_attention: n_layers=%d not in [1,%d]",
                   n_layers, WCA_MAX_LAYERS);
@@ -118,7 +119,12 @@ int wca_capture_attention(const float *const *h_q_layers, const float *const *h_
             return WCA_ERR_NO_DEVICE;
         }
         return launch_capture_tc(h_q_layers, h_k_layers, n_layers, n_heads_per_layer, ld_q, ld_k, q_rows, k_rows, d_utts, n_utts,
-                                 max_tokens, max_frames, medfilt_width, qk_scale, d_ws, flags, sms, st);
+                                 max_tokens, max_frames, medfilt_width, qk_scale, d_ws, d_partials, flags, sms, st);
+    }
+    if (d_partials != nullptr) {
+        set_error("wca_capture_attention: head-score partials are only produced by the tcgen05 kernel "
+                  "(ask wca_capture_writes_partials first)");
+        return WCA_ERR_UNSUPPORTED;
     }
     rc = launch_capture_logits_simt(h_q_layers, h_k_layers, n_layers, n_heads_per_layer, ld_q, ld_k, d_utts, n_utts,
                                     max_tokens, d_ws, st);
@@ -165,6 +171,26 @@ int wca_add_layernorm(const float *d_x, const float *d_h, const float *d_gamma, 
                   "wca_add_layernorm: pointers must be 16-byte aligned");
     if (n_rows == 0) return WCA_OK;
     return launch_add_layernorm(d_x, d_h, d_gamma, d_beta, d_y, d_n, n_rows, width, eps, static_cast<cudaStream_t>(stream));
+}
+
+int wca_capture_writes_partials(int max_frames, int medfilt_width, unsigned flags) {
+    return !(flags & (WCA_CAPTURE_FORCE_SIMT | WCA_CAPTURE_RAW_LOGITS)) && capture_tc_supported(0, max_frames, medfilt_width) ? 1 : 0;
+}
+
+int64_t wca_capture_partials_floats(int n_heads, int n_tokens, int n_frames) {
+    if (n_heads <= 0 || n_tokens <= 0 || n_frames <= 0) return 0;
+    const int64_t token_blocks = (n_tokens + 127) / 128;
+    return (int64_t)n_heads * token_blocks * (1 + (int64_t)n_frames);
+}
+
+int wca_head_scores_from_partials(const float *d_partials, const wca_utt_t *d_utts, int n_utts, int n_heads, float w_colnorm,
+                                  float w_rownorm, float *d_scores, wca_stream_t stream) {
+    WCA_CHECK_ARG(d_partials && d_utts && d_scores, "wca_head_scores_from_partials: null pointer");
+    WCA_CHECK_ARG(n_heads >= 1 && n_heads <= 65535 * 4 && n_utts >= 0 && n_utts <= 65535,
+                  "wca_head_scores_from_partials: bad geometry (%d heads, %d utts)", n_heads, n_utts);
+    if (n_utts == 0) return WCA_OK;
+    return launch_scores_from_partials(d_partials, d_utts, n_utts, n_heads, w_colnorm, w_rownorm, d_scores,
+                                       static_cast<cudaStream_t>(stream));
 }
 
 void wca_debug_enc_attn_buffer(float *d_buf) { set_enc_attn_debug_buffer(d_buf); }

@@ -72,8 +72,10 @@ constexpr int kOffQLo = kOffQHi + kQBytes;
 constexpr int kOffKHi = kOffQLo + kQBytes;
 constexpr int kOffKLo = kOffKHi + kKBytes;
 constexpr int kOffTile = kOffKLo + kKBytes;                     // 8 epilogue warps x 32 x 17 floats
-constexpr int kOffStat = kOffTile + 8 * 32 * kTilePitch * 4;    // [group][tile parity][m | sum][128]
-constexpr int kOffBar = kOffStat + 8 * kRows * 4;
+constexpr int kOffStat = kOffTile + 8 * 32 * kTilePitch * 4;    // [group][tile parity][128] x {m, sum, sum of squares, -}
+constexpr int kOffColSs = kOffStat + 2 * 2 * kRows * 16;        // [group][epilogue warp][224]: column sums of squares of a tile
+constexpr int kOffRed = kOffColSs + 2 * 4 * kMaxOwn * 4;        // [group][4] warp partials of the tile reductions
+constexpr int kOffBar = kOffRed + 2 * 4 * 4;
 enum Bar {
     kKFull = 0,                  // TMA -> splitters (transaction bytes): K slab landed
     kQFull = kKFull + 1,         // ... Q tile landed
@@ -115,6 +117,7 @@ struct TensorMaps {
 struct KernelArgs {
     const wca_utt_t *utts;
     float *ws;
+    float *partials;  // head-score partials (see wca_capture_attention), or nullptr
     int n_heads, lh_count, tok_blocks, n_tiles;
     float s, qk_scale;
     int raw_logits;
@@ -133,6 +136,8 @@ struct Geo {
     int layer, col0;         // decoder layer and first float column of the head
     int qrow0, krow0;        // first Q row of the tile / first K row of the utterance
     float *out;              // row 0 of this tile, frame 0
+    float *row_part;         // head-score partials of this tile: sum_t ||p[t,:]||_2 over its token rows (one float) ...
+    float *col_ss;           // ... and sum_t p[t,f]^2 over its token rows, frame 0 (F floats); nullptr: not wanted
 };
 
 template <int W>
@@ -152,6 +157,14 @@ __device__ __forceinline__ Geo decode_tile(const KernelArgs &a, int tile, uint32
     g.qrow0 = (int)u.q_row0 + t0;
     g.krow0 = (int)u.k_row0;
     g.out = a.ws + u.ws_off + ((int64_t)lh * g.T + t0) * g.F;
+    g.row_part = g.col_ss = nullptr;
+    if (a.partials != nullptr && !a.raw_logits) {
+        // per utterance: [lh][token block] row terms, then [lh][token block][F] column sums of squares
+        const int tbu = (g.T + kRows - 1) / kRows;
+        float *base = a.partials + u.part_off;
+        g.row_part = base + (int64_t)lh * tbu + tb;
+        g.col_ss = base + (int64_t)a.lh_count * tbu + ((int64_t)lh * tbu + tb) * g.F;
+    }
     const int slab = (((g.F + (int)csize - 1) / (int)csize) + 15) & ~15;
     g.f0 = (int)crank * slab;
     g.f1 = min(g.F, g.f0 + slab);
@@ -240,7 +253,7 @@ __device__ __forceinline__ void median_block(const float (&ptail)[Tail<W>::kLen]
 // the filter has run, so the block after next is loaded straight into its registers: the caller alternates the
 // roles of the two buffers instead of moving 32 registers per block.
 struct RowStats {
-    float m2, row_sum;
+    float m2, row_sum, row_ss;  // lazy reference (log2 domain), sum of e = 2^(y - m2), sum of e^2
 };
 template <int W>
 __device__ __forceinline__ void filter_exp_block(uint32_t trow, int b, int b_lo, int n_blocks, int tail, bool filter,
@@ -283,6 +296,7 @@ __device__ __forceinline__ void filter_exp_block(uint32_t trow, int b, int b_lo,
         const float f = need ? ex2_approx(st.m2 - bmax) : 1.f;
         if (need) st.m2 = bmax;
         st.row_sum *= f;
+        st.row_ss *= f * f;
 #pragma unroll 1
         for (int bb = b_lo; bb < b; ++bb) {
             float t[16];
@@ -303,6 +317,16 @@ __device__ __forceinline__ void filter_exp_block(uint32_t trow, int b, int b_lo,
     }
     st.row_sum += ((med[0] + med[1]) + (med[2] + med[3])) + ((med[4] + med[5]) + (med[6] + med[7])) +
                   (((med[8] + med[9]) + (med[10] + med[11])) + ((med[12] + med[13]) + (med[14] + med[15])));
+    {
+        // sum of squares of the row (head scores, timing.py:24: ||a[t,:]||_2 = sqrt(sum e^2) / sum e); two chains
+        float q0 = med[0] * med[0], q1 = med[1] * med[1];
+#pragma unroll
+        for (int i = 2; i < 16; i += 2) {
+            q0 = __fmaf_rn(med[i], med[i], q0);
+            q1 = __fmaf_rn(med[i + 1], med[i + 1], q1);
+        }
+        st.row_ss += q0 + q1;
+    }
     tmem_st16(trow + (uint32_t)(16 * b), med);
     tmem_ld_wait(cur);  // the block after next has landed (also orders the loads of the rescale path)
 }
@@ -328,7 +352,8 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
     const bool sweep = rows_live && b_lo < b_hi;
     const uint32_t trow = acc + ((uint32_t)(ewarp * 32) << 16) + kOwnCol0;  // own frame 0 of this lane quarter
     const int tail = g.n_own - 16 * (n_blocks - 1);  // valid columns of the last block (1..16)
-    float *sstat = reinterpret_cast<float *>(smem + kOffStat) + grp * 4 * kRows;  // [tile parity][m | sum][128]
+    float4 *sstat = reinterpret_cast<float4 *>(smem + kOffStat) + grp * 2 * kRows;  // [tile parity][128] x {m, sum, ss, -}
+    float row_term = 0.f;  // ||p[row,:]||_2 of the full row, in the one thread that reports it (head scores)
     const uint32_t bar_xmax = smem_u32(smem + kOffBar) + 8u * (kXMax + grp);
 
     float inv_sum = a.s;  // raw-logit mode: only the 2^-3 of the operand scaling is applied
@@ -349,7 +374,7 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
         // memory instead of two and a single exchange of (m, sum) pairs between column halves / cluster ranks.
         const float kLog2e = 1.4426950408889634f;
         const float scale2 = a.qk_scale * kLog2e;
-        RowStats st{-INFINITY, 0.f};
+        RowStats st{-INFINITY, 0.f, 0.f};
         if (sweep) {
             float ptail[Tail<W>::kLen], bufa[16], bufb[16];
             {
@@ -371,48 +396,64 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
             }
             tmem_wait_st();
         }
-        const float m2 = st.m2, row_sum = st.row_sum;
+        const float m2 = st.m2, row_sum = st.row_sum, row_ss = st.row_ss;
         stamp(tr, seq, kEvEpiA);
         stamp(tr, seq, kEvEpiXMax);
         stamp(tr, seq, kEvEpiB);
-        // (m, sum) of the other column half (mirrored tiles) and of the other cluster ranks; the statistics
-        // buffers alternate with the tile parity so that nobody overwrites a pair a slower peer still reads
-        float2 *spair = reinterpret_cast<float2 *>(sstat + x_parity * 2 * kRows);  // {m, sum} per slot
-        float gmax = m2, gsum = row_sum;
+        // (m, sum, sum of squares) of the other column half (mirrored tiles) and of the other cluster ranks; the
+        // statistics buffers alternate with the tile parity so that nobody overwrites a triple a slower peer still reads
+        float4 *strip = sstat + x_parity * kRows;
+        float gmax = m2, gsum = row_sum, gss = row_ss;
         if (g.dup) {
-            spair[ewarp * 32 + lane] = make_float2(m2, row_sum);
+            strip[ewarp * 32 + lane] = make_float4(m2, row_sum, row_ss, 0.f);
             named_bar_sync(1 + grp, kEpiThreads);
-            const float2 o = spair[(ewarp ^ 2) * 32 + lane];
+            const float4 o = strip[(ewarp ^ 2) * 32 + lane];
             gmax = fmaxf(m2, o.x);
-            gsum = (m2 > -INFINITY ? row_sum * ex2_approx(m2 - gmax) : 0.f) + (o.x > -INFINITY ? o.y * ex2_approx(o.x - gmax) : 0.f);
+            const float fa = m2 > -INFINITY ? ex2_approx(m2 - gmax) : 0.f, fb = o.x > -INFINITY ? ex2_approx(o.x - gmax) : 0.f;
+            gsum = row_sum * fa + o.y * fb;
+            gss = row_ss * (fa * fa) + o.z * (fb * fb);
         }
         if (csize > 1) {
             // every CTA of the cluster takes part, even with no own frames
-            spair[row] = row_ok ? make_float2(m2, row_sum) : make_float2(-INFINITY, 0.f);
+            strip[row] = row_ok ? make_float4(m2, row_sum, row_ss, 0.f) : make_float4(-INFINITY, 0.f, 0.f, 0.f);
             named_bar_sync(1 + grp, kEpiThreads);
             // lane r of the first warp signals rank r: ONE instruction with csize active lanes.  A loop of release-arrives
             // in one thread paid the cluster-scope release (~1.2 k cycles) once per rank, 9-10 k cycles per head.
             if ((uint32_t)row < csize) mbar_arrive_remote(bar_xmax, (uint32_t)row);
             mbar_wait_cluster(bar_xmax, x_parity);
-            // all ranks' pairs in flight at once: a dependent chain of remote loads (maximum first, then a conditional
+            // all ranks' triples in flight at once: a dependent chain of remote loads (maximum first, then a conditional
             // load of each sum) cost ~16 distributed-shared-memory round trips per head, 10.8 k of a 22.7 k-cycle epilogue
-            float2 pr[8];
+            float4 pr[8];
 #pragma unroll
             for (uint32_t r = 0; r < 8; ++r)
-                if (r < csize) pr[r] = ld_dsmem_f32x2(&spair[row], r);
+                if (r < csize) pr[r] = ld_dsmem_f32x4(&strip[row], r);
             gmax = -INFINITY;
 #pragma unroll
             for (uint32_t r = 0; r < 8; ++r)
                 if (r < csize) gmax = fmaxf(gmax, pr[r].x);
-            gsum = 0.f;
+            gsum = gss = 0.f;
 #pragma unroll
             for (uint32_t r = 0; r < 8; ++r)
-                if (r < csize && pr[r].x > -INFINITY) gsum += pr[r].y * ex2_approx(pr[r].x - gmax);
+                if (r < csize && pr[r].x > -INFINITY) {
+                    const float f = ex2_approx(pr[r].x - gmax);
+                    gsum += pr[r].y * f;
+                    gss += pr[r].z * (f * f);
+                }
         }
+        // exactly one thread per token row reports the row norm: rank 0 of a cluster, the first copy of a mirrored row
+        if (g.row_part != nullptr && row_ok && (csize == 1 || cluster_ctarank() == 0) && (!g.dup || ewarp < 2))
+            row_term = sqrtf(gss) / gsum;
         inv_sum = (m2 > -INFINITY ? ex2_approx(m2 - gmax) : 0.f) / gsum;  // this thread's e values are relative to its own m
+        // lanes past the last token row hold finite values nobody stores; as exact zeros in the transposition tile they also
+        // drop out of the column sums of the head scores without a per-element predicate
+        if (g.col_ss != nullptr && !row_ok) inv_sum = 0.f;
         stamp(tr, seq, kEvEpiXSum);
     }
 
+    // column partials of this warp's rows for the head scores: [group][epilogue warp][own frame]
+    float *colss = g.col_ss != nullptr ? reinterpret_cast<float *>(smem + kOffColSs) + (grp * 4 + ewarp) * kMaxOwn : nullptr;
+    if (colss != nullptr && !g.dup && csize == 1)
+        named_bar_sync(1 + grp, kEpiThreads);  // nobody still sums the previous tile's partials (see the end of this function)
     // sweep C: normalise, transpose 32x16 blocks through shared memory, coalesced row stores.
     // Lane (c, rsel) stores column c of rows rsel, rsel+2, ...: two 64-byte row segments per
     // instruction, the address advancing by two rows per step.
@@ -464,11 +505,45 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
                         if (k < n_steps) st_stream(obase + (o0 + k * step), o[k]);
                 }
             }
+            if (colss != nullptr) {
+                // head scores (timing.py:21): sum over this warp's token rows of p[t,f]^2 for the 16 frames of the block;
+                // lane (c, rsel) holds rows rsel, rsel + 2, ...: rows past the last token row are exact zeros in the tile
+                float q0 = o[0] * o[0], q1 = o[1] * o[1];
+#pragma unroll
+                for (int k = 2; k < 16; k += 2) {
+                    q0 = __fmaf_rn(o[k], o[k], q0);
+                    q1 = __fmaf_rn(o[k + 1], o[k + 1], q1);
+                }
+                float q = q0 + q1;
+                q += __shfl_xor_sync(0xffffffffu, q, 16);
+                if (lane < 16) colss[16 * b + lane] = q;
+            }
             __syncwarp();
             tmem_ld_wait(v);
         }
     }
     stamp(tr, seq, kEvEpiC);
+    if (g.col_ss != nullptr) {
+        // ---- head-score partials of the tile (replaces a second full read of the maps by wca_head_scores) ----
+        // row term: fixed shuffle tree per warp, warps added in order by one thread (deterministic)
+        float *red = reinterpret_cast<float *>(smem + kOffRed) + grp * 4;
+        const float wsum = warp_sum(row_term);
+        if (lane == 0) red[ewarp] = wsum;
+        named_bar_sync(1 + grp, kEpiThreads);  // column partials and warp sums of all four warps are in shared memory
+        const int t = ewarp * 32 + lane;
+        if (t == 0 && (csize == 1 || cluster_ctarank() == 0)) *g.row_part = ((red[0] + red[1]) + red[2]) + red[3];
+        const float *cs = reinterpret_cast<const float *>(smem + kOffColSs) + grp * 4 * kMaxOwn;
+        const int live_warps = min(g.dup ? 2 : 4, (g.rows_valid + 31) >> 5);  // logical 32-row groups with token rows
+        for (int col = t; col < g.n_own; col += kEpiThreads) {
+            // mirrored tiles: warps 0/1 swept the first `split` blocks of the row groups 0/1, warps 2/3 the rest
+            const int w0 = (g.dup && (col >> 4) >= split) ? 2 : 0;
+            float acc = 0.f;
+            for (int w = 0; w < live_warps; ++w) acc += cs[(w0 + w) * kMaxOwn + col];  // fixed order
+            g.col_ss[g.f0 + col] = acc;
+        }
+        // the partials are overwritten by the group's next tile in ITS store sweep, which sits behind that tile's
+        // statistics-exchange barrier (mirrored and cluster tiles) or behind the barrier plain tiles take before the sweep
+    }
     return released;
 }
 
@@ -749,8 +824,8 @@ static int encode_map(EncodeTiledFn encode, CUtensorMap *map, const float *base,
 
 int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_layers, int n_layers, int n_heads,
                       int64_t ld_q, int64_t ld_k, int64_t q_rows, int64_t k_rows, const wca_utt_t *d_utts, int n_utts,
-                      int max_tokens, int max_frames, int medfilt_width, float qk_scale, float *d_ws, unsigned flags,
-                      int sm_count, cudaStream_t stream) {
+                      int max_tokens, int max_frames, int medfilt_width, float qk_scale, float *d_ws, float *d_partials,
+                      unsigned flags, int sm_count, cudaStream_t stream) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
@@ -826,6 +901,7 @@ int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_la
     tc::KernelArgs a;
     a.utts = d_utts;
     a.ws = d_ws;
+    a.partials = d_partials;
     a.n_heads = n_heads;
     a.lh_count = lh_count;
     a.tok_blocks = tok_blocks;

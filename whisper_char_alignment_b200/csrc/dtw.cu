@@ -533,6 +533,240 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_multi_kernel(const DtwLaun
     }
 }
 
+// ---- long problems: lanes own strips of 16 FRAMES and sweep DOWN the text rows --------------------------------
+// The row-strip kernels above read the cost matrix against its layout (one 4-byte load per lane and text row, 32
+// cache lines per warp load) and keep that load on the dependency chain; for LibriSpeech-shaped problems (401 x 1500)
+// they ran at ~400 ns per wavefront step.  Here the recurrence is swept the other way round: lane g owns frames
+// 16g .. 16g+15 (94 lanes = 3 warps for 1500 frames) and handles text row i at step s = i + g, so
+//   * a warp reads 2 KB of ONE matrix row per step, contiguous, each lane its own 64 bytes, with cp.async straight into a
+//     private ring in shared memory kLongAhead rows ahead (every lane consumes what it loaded itself: no flags, no
+//     barriers, just cp.async.wait_group);
+//   * the sweep has N + lanes - 1 steps (~500) instead of M + lanes - 1 (~1630);
+//   * the trace word of a step is the 16 two-bit codes of the strip: N x lanes 32-bit words in shared memory
+//     (172 KB for the largest legal problem), walked by one thread with bit scans: one dependent shared-memory read
+//     per text row plus one per 16 consecutive time steps.
+// The cell rule, the fp32 add and therefore every path are those of the other kernels (and of dtw_cpu), bit for bit.
+constexpr int kStripCols = 16;
+constexpr int kLongAhead = 4;               // rows in flight per lane
+constexpr int kLongSlots = kLongAhead + 1;  // ring slots: the row being read is never the one being refilled
+
+__device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gmem_src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async4_zfill(void *smem_dst, const void *gmem_src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(src_bytes)
+                 : "memory");
+}
+
+struct LongPlan {
+    int wpp;       // warps per problem (lanes = 32 * wpp >= ceil(max_frames / 16))
+    size_t jump, edge, ring, trace, smem;
+};
+static LongPlan dtw_long_plan(int max_rows, int max_frames) {
+    LongPlan l;
+    const int lanes_needed = (max_frames + kStripCols - 1) / kStripCols;
+    l.wpp = (lanes_needed + 31) / 32;
+    const size_t lanes = 32 * (size_t)l.wpp;
+    l.jump = (size_t)((max_rows + 3) & ~3) * 4;
+    l.edge = ((size_t)(l.wpp - 1) * (size_t)max_rows * 8 + 15) & ~(size_t)15;
+    l.ring = (size_t)kLongSlots * 4 * lanes * 16;
+    l.trace = (size_t)max_rows * lanes * 4;
+    l.smem = l.jump + l.edge + l.ring + l.trace;
+    return l;
+}
+
+template <int WPP>
+__global__ void __launch_bounds__(32 * WPP) dtw_align_long_kernel(const DtwLaunch p, int max_rows) {
+    constexpr int L = 32 * WPP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = threadIdx.x;
+    const int prob = blockIdx.x;
+    const wca_utt_t u = p.utts[prob];
+    const int N = u.row_end - u.row_begin;
+    const int M = u.n_frames;
+    // shared memory: [jump frames][edge words (WPP-1) x max_rows][cost ring kLongSlots x 4 x L float4][trace N x L words]
+    int32_t *jump_s = reinterpret_cast<int32_t *>(smem_raw);
+    const size_t jump_bytes = (size_t)((max_rows + 3) & ~3) * 4;
+    const size_t edge_bytes = ((size_t)(WPP - 1) * max_rows * 8 + 15) & ~(size_t)15;
+    unsigned long long *edge = reinterpret_cast<unsigned long long *>(smem_raw + jump_bytes);
+    float4 *ring = reinterpret_cast<float4 *>(smem_raw + jump_bytes + edge_bytes);
+    uint32_t *trace = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(ring) + (size_t)kLongSlots * 4 * L * 16);
+    if (N <= 0 || M <= 0) {
+        if (g == 0 && p.path_len) p.path_len[prob] = 0;
+        return;
+    }
+    for (int r = g; r < N; r += L) jump_s[r] = -1;
+    for (int e = g; e < (WPP - 1) * N; e += L) edge[e] = 0ull;  // tag 0 = not yet published
+    __syncthreads();
+
+    const float *xg = p.matrix + u.matrix_off;
+    const int j0 = g * kStripCols;                       // first frame of the strip
+    const int n_cols = max(0, min(kStripCols, M - j0));  // frames of the strip inside the matrix
+    const bool flip = p.negate != 0;
+    // every matrix row starts 16-byte aligned (base aligned, M % 4 == 0): 16-byte copies; else 4-byte copies
+    const bool vec = (reinterpret_cast<uintptr_t>(xg) & 15) == 0 && (M & 3) == 0;
+    // ring slot of row i: i % kLongSlots; chunk q of the strip at ring[(slot * 4 + q) * L + g] (conflict-free 16-byte reads)
+    auto prefetch = [&](int i) {
+        if (i >= 0 && i < N && n_cols > 0) {
+            const float *src = xg + (int64_t)i * M + j0;
+            float4 *dst = ring + (size_t)((i % kLongSlots) * 4) * L + g;
+            if (vec) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int valid = max(0, min(4, n_cols - 4 * q));
+                    cp_async16_zfill(dst + q * L, valid > 0 ? src + 4 * q : xg, 4 * valid);  // bytes past `valid` are zero-filled
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kStripCols; ++k)
+                    cp_async4_zfill(reinterpret_cast<float *>(dst + (k >> 2) * L) + (k & 3), k < n_cols ? src + k : xg, k < n_cols ? 4 : 0);
+            }
+        }
+        cp_async_commit();
+    };
+
+    // cost[i-1][j] of the strip's frames (table row above), +inf before the first row; a lane that has not started keeps
+    // +inf (inf + 0: its x reads as 0 until its first row), a lane past the last row computes values nobody reads
+    float up[kStripCols];
+#pragma unroll
+    for (int k = 0; k < kStripCols; ++k) up[k] = INFINITY;
+    float last_new = INFINITY;                      // cost[i][j0 + 15] of the row just finished (what the right neighbour needs)
+    float diag_in = (g == 0) ? 0.f : INFINITY;      // cost[i-1][j0 - 1]: table cell (0, 0) = 0 for the first strip's first row
+    const volatile unsigned long long *edge_in = edge + (size_t)(warp > 0 ? warp - 1 : 0) * N;
+    volatile unsigned long long *edge_out = edge + (size_t)(warp < WPP - 1 ? warp : 0) * N;
+    const bool warp_live = warp * 32 * kStripCols < M;  // warps whose strips all lie past the last frame only idle along
+
+    // copy group n of a lane carries its row n - g: kLongAhead groups before the loop, one more per step
+#pragma unroll
+    for (int a = 0; a < kLongAhead; ++a) prefetch(a - g);
+    const int n_steps = N + L - 1;
+    if (warp_live)
+    for (int s = 0; s < n_steps; ++s) {
+        const int i = s - g;  // text row of this lane at this step
+        const bool act = (unsigned)i < (unsigned)N;
+        // left neighbour's newest last cell = cost[i][j0 - 1]
+        float left_in = __shfl_up_sync(0xffffffffu, last_new, 1);
+        if (lane == 0) {
+            left_in = INFINITY;  // table column 0
+            if (warp > 0 && act) {
+                unsigned long long w = edge_in[i];
+                for (uint32_t spins = 0; (uint32_t)(w >> 32) != (uint32_t)(i + 1); ++spins) {
+                    if (spins > (1u << 26)) __trap();  // a protocol bug must surface as a launch failure, not a hung GPU
+                    w = edge_in[i];
+                }
+                left_in = __uint_as_float((uint32_t)w);
+            }
+        }
+        cp_async_wait<kLongAhead - 1>();  // this lane's copy of row i has landed
+        float x[kStripCols];
+        {
+            const float4 *slot = ring + (size_t)((act ? i % kLongSlots : 0) * 4) * L + g;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 v = act ? slot[q * L] : make_float4(0.f, 0.f, 0.f, 0.f);
+                x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+            }
+        }
+        prefetch(i + kLongAhead);  // into the slot read one step ago, never the one just read
+        uint32_t tw = 0;
+        float c0 = diag_in;   // cost[i-1][j-1]
+        float c2 = left_in;   // cost[i][j-1]
+#pragma unroll
+        for (int k = 0; k < kStripCols; ++k) {
+            const float c1 = up[k];  // cost[i-1][j]
+            // dtw_cpu's rule: the diagonal only if strictly below both others, then the text step only if strictly below
+            // both others, else the time step (ties and NaN).  The part that does not involve c2 is off the chain.
+            const bool lt01 = c0 < c1, lt10 = c1 < c0;
+            const float a = lt01 ? c0 : c1;           // the only candidate that can beat c2
+            const bool win = (lt01 | lt10) & (a < c2);
+            const float cm = win ? a : c2;
+            const uint32_t code = win ? (lt01 ? 0u : 1u) : 2u;
+            tw |= code << (2 * k);
+            const float xv = flip ? -x[k] : x[k];
+            const float cost = __fadd_rn(xv, cm);
+            c0 = c1;       // this column's old value is the next column's diagonal
+            c2 = cost;     // this column's new value is the next column's left
+            up[k] = cost;
+        }
+        diag_in = left_in;
+        last_new = c2;
+        if (act) {
+            if (n_cols > 0) trace[(size_t)i * L + g] = tw;
+            if (lane == 31 && warp < WPP - 1)
+                edge_out[i] = ((unsigned long long)(uint32_t)(i + 1) << 32) | __float_as_uint(last_new);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // ---- backtrace by one thread: per text row, the nearest cell at or left of the current frame whose step leaves the row
+    if (g == 0) {
+        if (!p.path_text) {
+            int row = N - 1, col = M - 1, n_diag = 0;
+            while (row >= 0 && col >= 0) {
+                int wi = col >> 4;
+                const int kc = col & 15;
+                uint32_t w = trace[(size_t)row * L + wi];
+                uint32_t leave = ~w & 0xAAAAAAAAu;                      // bit 2k+1 set where code k is 0 or 1
+                if (kc < 15) leave &= (1u << (2 * kc + 2)) - 1u;        // cells at or left of the current frame
+                while (leave == 0u && wi > 0) {
+                    --wi;
+                    w = trace[(size_t)row * L + wi];
+                    leave = ~w & 0xAAAAAAAAu;
+                }
+                if (leave == 0u) break;  // left border: the remaining rows keep -1 (upstream's index arithmetic gives frame -1)
+                const int k = (31 - __clz(leave)) >> 1;
+                const uint32_t code = (w >> (2 * k)) & 3u;
+                const int at = wi * kStripCols + k;
+                jump_s[row] = at;       // first path point of the text row
+                n_diag += code == 0u;
+                col = at - (code == 0u);
+                --row;
+            }
+            if (p.path_len) p.path_len[prob] = N + M - n_diag;  // every diagonal step saves one path point
+        } else {
+            const int cap = N + M;
+            int32_t *pt = p.path_text + u.path_off, *pj = p.path_time + u.path_off;
+            int bi = N, bj = M, pos = cap;
+            while (bi > 0 || bj > 0) {
+                --pos;
+                pt[pos] = bi - 1;
+                pj[pos] = bj - 1;
+                uint32_t code;
+                if (bj == 0) code = 1u;
+                else if (bi == 0) code = 2u;
+                else code = (trace[(size_t)(bi - 1) * L + ((bj - 1) >> 4)] >> (2 * ((bj - 1) & 15))) & 3u;
+                if (code != 2u && bi >= 1) jump_s[bi - 1] = bj - 1;
+                if (code == 0u) {
+                    --bi;
+                    --bj;
+                } else if (code == 1u) {
+                    --bi;
+                } else {
+                    --bj;
+                }
+            }
+            if (p.path_len) p.path_len[prob] = cap - pos;
+        }
+    }
+    __syncthreads();
+
+    if (p.jump_frames)
+        for (int r = g; r < N; r += L) p.jump_frames[u.jump_off + r] = jump_s[r];
+    if (p.word_bounds && p.start_times && p.end_times) {
+        const int32_t *wb = p.word_bounds + u.word_off;
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        for (int w = g; w < u.n_words; w += L) {
+            const int a = wb[w], b = wb[w + 1];
+            p.start_times[u.word_off + w] = (a >= 0 && a < N) ? (double)jump_s[a] / WCA_TOKENS_PER_SECOND : nan;
+            p.end_times[u.word_off + w] = (b >= 0 && b < N) ? (double)jump_s[b] / WCA_TOKENS_PER_SECOND : nan;
+        }
+    }
+}
+
 // Geometry of the multi-warp variant for a launch (0 warps: use the warp-per-problem kernel).
 struct MultiPlan {
     int wpp, r;
@@ -607,7 +841,16 @@ static DtwPlan dtw_plan(int max_rows, int max_frames) {
     return pl;
 }
 
+// The column-strip kernel takes every launch whose problems are long (more than 128 text rows) or too large to stage
+// next to their trace, as long as its own trace (max_rows x lanes words) fits in shared memory.
+static bool use_long_kernel(int max_rows, int max_frames) {
+    const LongPlan lp = dtw_long_plan(max_rows, max_frames);
+    if (lp.wpp > 4 || lp.smem > kSmemBudget) return false;
+    return max_rows > 128 || !dtw_plan(max_rows, max_frames).staged;
+}
+
 int64_t dtw_workspace_bytes(int n_utts, int max_rows, int max_frames) {
+    if (use_long_kernel(max_rows, max_frames)) return 0;
     const MultiPlan m = dtw_multi_plan(max_rows, max_frames);
     if (m.wpp && n_utts <= 48) return m.trace_in_smem ? 0 : (int64_t)n_utts * (int64_t)m.trace;  // same rule as the launch
     if (dtw_plan(max_rows, max_frames).trace_in_smem) return 0;
@@ -631,6 +874,15 @@ static int launch_multi_a(const DtwLaunch &p, size_t smem, cudaStream_t stream) 
 template <int R, int WPP>
 static int launch_multi(const DtwLaunch &p, size_t smem, cudaStream_t stream) {
     return launch_multi_a<R, WPP, 4>(p, smem, stream);  // 4 columns of lookahead (1..8 measured the same)
+}
+
+template <int WPP>
+static int launch_long(const DtwLaunch &p, int max_rows, size_t smem, cudaStream_t stream) {
+    if (smem > 48u * 1024u)
+        WCA_CUDA(cudaFuncSetAttribute(dtw_align_long_kernel<WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dtw_align_long_kernel<WPP><<<p.n_utts, 32 * WPP, smem, stream>>>(p, max_rows);
+    WCA_LAUNCH_CHECK("dtw_align_long_kernel");
+    return WCA_OK;
 }
 
 template <int R, bool kTraceSmem, bool kStaged>
@@ -674,6 +926,20 @@ int launch_dtw_align(const float *d_matrix, const wca_utt_t *d_utts, int n_utts,
     p.end_times = d_end_times;
     p.trace_ws = nullptr;
     p.jump_stride = (max_rows + 3) & ~3;
+    if (use_long_kernel(max_rows, max_frames)) {
+        const LongPlan lp = dtw_long_plan(max_rows, max_frames);
+        p.trace_stride = (int64_t)lp.trace;
+        p.trace_in_smem = 1;
+        p.staged = p.ring = 0;
+        p.xs_floats = 0;
+        p.warps = 1;
+        switch (lp.wpp) {
+            case 1: return launch_long<1>(p, max_rows, lp.smem, stream);
+            case 2: return launch_long<2>(p, max_rows, lp.smem, stream);
+            case 3: return launch_long<3>(p, max_rows, lp.smem, stream);
+            default: return launch_long<4>(p, max_rows, lp.smem, stream);
+        }
+    }
     const MultiPlan mp = dtw_multi_plan(max_rows, max_frames);
     // long texts, few problems: several warps per problem shorten the dependency chain of each one; with many
     // problems in flight the warp-per-problem kernel has the higher throughput (64 x (401 x 1500): 1.48 vs 1.69 ms)

@@ -126,6 +126,40 @@ __global__ void __launch_bounds__(256) head_scores_kernel(const float *__restric
     }
 }
 
+// Head scores from the partials the capture kernel leaves behind (wca_capture_attention with d_partials): per
+// (utterance, head, block of 128 tokens) the row term sum_t ||p[t,:]||_2 and the F column sums of squares.  One warp
+// per (utterance, head): sum_f sqrt(sum over token blocks) in a fixed order -- no second read of the maps.
+// grid (ceil(n_heads / 4), n_utts), block 128.
+__global__ void __launch_bounds__(128) scores_from_partials_kernel(const float *__restrict__ partials,
+                                                                   const wca_utt_t *__restrict__ utts, int n_heads,
+                                                                   float w_col, float w_row, float *__restrict__ scores) {
+    const wca_utt_t u = utts[blockIdx.y];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int head = blockIdx.x * 4 + warp;
+    if (head >= n_heads) return;
+    const int F = u.n_frames, tbu = (u.n_tokens + 127) / 128;
+    const float *row_part = partials + u.part_off + (int64_t)head * tbu;
+    const float *col_ss = partials + u.part_off + (int64_t)n_heads * tbu + (int64_t)head * tbu * F;
+    float col = 0.f;
+    if (w_col > 0.f)
+        for (int f = lane; f < F; f += kWarp) {
+            float ss = 0.f;
+            for (int tb = 0; tb < tbu; ++tb) ss += col_ss[(int64_t)tb * F + f];
+            col += sqrtf(ss);
+        }
+    col = warp_sum(col);
+    if (lane == 0) {
+        float score = 0.f;
+        if (w_col > 0.f) score += w_col * col;
+        if (w_row > 0.f) {
+            float row = 0.f;
+            for (int tb = 0; tb < tbu; ++tb) row += row_part[tb];
+            score += w_row * row;
+        }
+        scores[u.score_off + head] = score;
+    }
+}
+
 // grid (n_utts), block 256, dynamic smem n_heads floats.  Rank by counting with the
 // reference's tuple order (score, layer, head): ties go to the smaller head index.  The order must be TOTAL so that
 // every output slot is written exactly once: a NaN score (non-finite logits upstream) compares false both ways and
@@ -206,6 +240,14 @@ int launch_head_scores(const float *d_ws, const wca_utt_t *d_utts, int n_utts, i
     (void)max_frames;  // any row length: the kernel walks it in chunks of 256 columns
     head_scores_kernel<<<dim3(n_heads, n_utts), 256, 0, stream>>>(d_ws, d_utts, w_col, w_row, w_cov, d_scores);
     WCA_LAUNCH_CHECK("head_scores_kernel");
+    return WCA_OK;
+}
+
+int launch_scores_from_partials(const float *d_partials, const wca_utt_t *d_utts, int n_utts, int n_heads, float w_col,
+                                float w_row, float *d_scores, cudaStream_t stream) {
+    scores_from_partials_kernel<<<dim3((n_heads + 3) / 4, n_utts), 128, 0, stream>>>(d_partials, d_utts, n_heads, w_col,
+                                                                                      w_row, d_scores);
+    WCA_LAUNCH_CHECK("scores_from_partials_kernel");
     return WCA_OK;
 }
 

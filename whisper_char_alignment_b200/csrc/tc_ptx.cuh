@@ -46,6 +46,14 @@ __device__ __forceinline__ float2 ld_dsmem_f32x2(const float2 *local, uint32_t r
     return v;
 }
 
+__device__ __forceinline__ float4 ld_dsmem_f32x4(const float4 *local, uint32_t rank) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(map_to_rank(smem_u32(local), rank)));
+    return v;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }

@@ -88,6 +88,25 @@ def _as_f32_rows(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
+class _ScorePartials:
+    """Head-score partials of one utterance's maps, attached to the tensor get_attentions returns.  Valid only for
+    that very tensor object as long as nobody has written to it (the version counter is checked): a view, a copy or a
+    modified tensor is scored by reading the maps, like any other input."""
+
+    __slots__ = ("buffer", "offset", "version", "data_ptr", "shape")
+
+    def __init__(self, buffer, offset, maps):
+        self.buffer, self.offset = buffer, offset
+        self.version, self.data_ptr, self.shape = maps._version, maps.data_ptr(), tuple(maps.shape)
+
+    @staticmethod
+    def of(maps):
+        p = getattr(maps, "_wca_score_partials", None)
+        if p is None or p.version != maps._version or p.data_ptr != maps.data_ptr() or p.shape != tuple(maps.shape):
+            return None
+        return p
+
+
 def get_attentions_batch(mels, tokens_list: Sequence[torch.Tensor], model, tokenizer, max_frames_list,
                          medfilt_width: int = 7, qk_scale: float = 1.0, *, raw_logits: bool = False,
                          force_simt: bool = False):
@@ -129,15 +148,21 @@ def get_attentions_batch(mels, tokens_list: Sequence[torch.Tensor], model, token
     q_layers = [_as_f32_rows(q) for q in qs]
     k_layers = [_as_f32_rows(k) for k in ks]
 
+    flags = (_cabi.WCA_CAPTURE_RAW_LOGITS if raw_logits else 0) | (_cabi.WCA_CAPTURE_FORCE_SIMT if force_simt else 0)
+    # head-score partials: the capture epilogue holds every map value anyway, so it also leaves sum_t ||p[t,:]||_2 and
+    # the column sums of squares behind; force_align / filter_attention then score the heads without reading the maps
+    with_partials = _cabi.capture_writes_partials(max(frames), int(medfilt_width), flags)
     recs = np.zeros(B, dtype=_cabi.UTT_DTYPE)
-    off = 0
+    off = part_off = 0
     for b in range(B):
         recs[b]["n_tokens"], recs[b]["n_frames"] = lens[b], frames[b]
         recs[b]["q_row0"], recs[b]["k_row0"] = b * t_max, b * k_layers[0].shape[1]
         recs[b]["ws_off"] = off
+        recs[b]["part_off"] = part_off
         off += n_layers * n_heads * lens[b] * frames[b]
+        part_off += _cabi.capture_partials_floats(n_layers * n_heads, lens[b], frames[b]) if with_partials else 0
     ws = torch.empty(off, dtype=torch.float32, device=device)
-    flags = (_cabi.WCA_CAPTURE_RAW_LOGITS if raw_logits else 0) | (_cabi.WCA_CAPTURE_FORCE_SIMT if force_simt else 0)
+    partials = torch.empty(part_off, dtype=torch.float32, device=device) if with_partials else None
     # One launch per frame-count bucket: the capture kernel spreads an utterance's frames over a
     # cluster of 1/2/4/8 CTAs (224 frames each) and the cluster size is a launch parameter, so
     # short utterances must not share a launch with 30 s ones.
@@ -149,11 +174,14 @@ def get_attentions_batch(mels, tokens_list: Sequence[torch.Tensor], model, token
         d_utts = _cabi.upload_utts(sub, device)
         _cabi.capture_attention(q_layers, k_layers, n_heads, None, None, d_utts, len(members),
                                 int(sub["n_tokens"].max()), int(sub["n_frames"].max()), int(medfilt_width),
-                                float(qk_scale), ws, flags)
+                                float(qk_scale), ws, flags, partials)
     weights, logits = [], []
     for b in range(B):
         n = n_layers * n_heads * lens[b] * frames[b]
-        weights.append(ws[recs[b]["ws_off"]: recs[b]["ws_off"] + n].view(n_layers, n_heads, lens[b], frames[b]))
+        w = ws[recs[b]["ws_off"]: recs[b]["ws_off"] + n].view(n_layers, n_heads, lens[b], frames[b])
+        if with_partials:
+            w._wca_score_partials = _ScorePartials(partials, int(recs[b]["part_off"]), w)
+        weights.append(w)
         logits.append(out_logits[b, : lens[b]])
     return weights, logits
 
@@ -186,6 +214,11 @@ class _Plan:
 
     def __init__(self, ws_list, row_begin, n_sel_list, word_counts=None):
         self.B = B = len(ws_list)
+        # head-score partials left by the capture kernel: usable when every utterance carries valid ones in ONE buffer
+        parts = [_ScorePartials.of(w) for w in ws_list]
+        self.partials = None
+        if all(p is not None for p in parts) and all(p.buffer is parts[0].buffer for p in parts):
+            self.partials = parts[0].buffer
         self.device = ws_list[0].device
         self.base_ptr = ws_list[0].data_ptr()
         for w in ws_list:
@@ -218,6 +251,8 @@ class _Plan:
         recs["path_off"] = starts(n_rows + F)
         recs["jump_off"] = starts(n_rows)
         recs["word_off"] = starts(n_words + 1)
+        if self.partials is not None:
+            recs["part_off"] = [p.offset for p in parts]
         self.recs = recs
         self.totals = dict(score=int(heads.sum()), sel=int(n_sel.sum()), matrix=int((n_rows * F).sum()),
                            path=int((n_rows + F).sum()), jump=int(n_rows.sum()), word=int((n_words + 1).sum()))
@@ -232,8 +267,12 @@ def _score_and_select(plan: _Plan, w_colnorm, w_rownorm, w_coverage):
     scores = torch.empty(plan.totals["score"], dtype=torch.float32, device=dev)
     sel = torch.empty(max(plan.totals["sel"], 1), dtype=torch.int32, device=dev)
     sel_scores = torch.empty(max(plan.totals["sel"], 1), dtype=torch.float32, device=dev)
-    _cabi.head_scores(plan.base_ptr, plan.d_utts, plan.B, plan.n_heads, plan.max_tokens, plan.max_frames,
-                      w_colnorm, w_rownorm, w_coverage, scores)
+    if plan.partials is not None and not w_coverage > 0:
+        # the capture kernel already reduced the maps: finish the sums instead of reading the maps again
+        _cabi.head_scores_from_partials(plan.partials, plan.d_utts, plan.B, plan.n_heads, w_colnorm, w_rownorm, scores)
+    else:
+        _cabi.head_scores(plan.base_ptr, plan.d_utts, plan.B, plan.n_heads, plan.max_tokens, plan.max_frames,
+                          w_colnorm, w_rownorm, w_coverage, scores)
     _cabi.topk_heads(scores, plan.d_utts, plan.B, plan.n_heads, sel, sel_scores)
     return scores, sel, sel_scores
 

@@ -81,6 +81,11 @@ class _Conv(nn.Conv1d):
 #: output).  Same products, fewer launches: with BF16x9 emulation every GEMM first scans its operands for Inf/NaN, and
 #: `xa` (batch * 1500 rows) was scanned 2 * layers times.  False: one GEMM per nn.Linear, as the module tree suggests.
 FUSED_PROJECTIONS = os.environ.get("WCA_FUSED_PROJECTIONS", "1") != "0"
+#: decoder layers whose cross-attention K and V share one GEMM over the encoder output.  The output row pitch grows with
+#: the group (2 * group * d floats), and the kernels that read one layer's K / V out of it walk rows that far apart.
+#: Measured on a B200 (TIMIT-shaped batch of 32, one box, capture launch / attention / step): unfused 0.397 / 41.5 / 342.8 ms,
+#: group 1: 0.407 / 41.7 / 340.6, group 4: 0.408 / 41.8 / 338.7, all 24 layers: 0.447 / 42.4 / 342.9.
+CROSS_KV_GROUP = int(os.environ.get("WCA_CROSS_KV_GROUP", "4"))
 
 
 class _FusedWeights:
@@ -242,13 +247,14 @@ class TextDecoder(nn.Module):
         self.positional_embedding = nn.Parameter(torch.empty(n_ctx, width))
         self.blocks = nn.ModuleList([Block(width, heads, cross=True) for _ in range(layers)])
         self.ln = _Norm(width)
-        self._cross_kv = _FusedWeights()
+        self._cross_kv = {}
 
-    def cross_kv_all_layers(self, xa):
-        """K and V of every layer's cross-attention in ONE GEMM over the encoder output: (batch, n_ctx, 2 * layers * d),
-        layer l's K at columns [2l d, (2l+1) d), its V right after.  The kernels read the strided views in place."""
-        projections = [p for blk in self.blocks for p in (blk.cross_attn.key, blk.cross_attn.value)]
-        w, b = self._cross_kv.get(projections, xa.dtype)
+    def cross_kv(self, xa, first, count):
+        """K and V of the cross-attention of decoder layers [first, first + count) in ONE GEMM over the encoder output:
+        (batch, n_ctx, 2 * count * d), layer first + i's K at columns [2i d, (2i+1) d), its V right after.  The kernels
+        read the strided views in place."""
+        projections = [p for blk in self.blocks[first:first + count] for p in (blk.cross_attn.key, blk.cross_attn.value)]
+        w, b = self._cross_kv.setdefault((first, count), _FusedWeights()).get(projections, xa.dtype)
         return F.linear(xa, w, b)
 
     def forward(self, tokens, xa, tap=None):
@@ -256,12 +262,18 @@ class TextDecoder(nn.Module):
         x = self.token_embedding(tokens) + self.positional_embedding[: tokens.shape[-1]]
         x = x.to(xa.dtype)
         d = x.shape[-1]
-        kv_all = None
-        if FUSED_PROJECTIONS and xa.is_cuda and not torch.is_grad_enabled():
-            kv_all = self.cross_kv_all_layers(xa)
+        fused = FUSED_PROJECTIONS and CROSS_KV_GROUP > 0 and xa.is_cuda and not torch.is_grad_enabled()
+        # equal groups only: the capture kernel reads every layer's K with ONE row pitch
+        group = max(k for k in range(1, max(1, min(CROSS_KV_GROUP, len(self.blocks))) + 1) if len(self.blocks) % k == 0)
+        kv_group = None
         pending = None
         for l, blk in enumerate(self.blocks):
-            kv = None if kv_all is None else (kv_all[..., 2 * l * d:(2 * l + 1) * d], kv_all[..., (2 * l + 1) * d:(2 * l + 2) * d])
+            kv = None
+            if fused:
+                i = l % group
+                if i == 0:
+                    kv_group = self.cross_kv(xa, l, min(group, len(self.blocks) - l))
+                kv = (kv_group[..., 2 * i * d:(2 * i + 1) * d], kv_group[..., (2 * i + 1) * d:(2 * i + 2) * d])
             x, pending = blk(x, xa, causal=True, pending=pending, kv=kv, tap=tap)
         x = _add_ln(x, pending, self.ln)[1]
         return self._vocab_logits(x)
