@@ -89,8 +89,9 @@ WCA_API int wca_device_info(int *sm_count, int *compute_capability);
  * Output: d_ws + ws_off, layout (L, H, T, F) fp32, exactly what get_attentions returns.
  * d_partials (may be NULL): head-score partials for wca_head_scores_from_partials, so that scoring the heads
  * (timing.py:17-34) does not read the maps a second time.  Per utterance, at d_partials + part_off, with
- * B = ceil(T / 128) token blocks: [L*H][B] floats sum_t ||p[t,:]||_2 over the rows of the block, then
- * [L*H][B][F] floats sum_t p[t,f]^2 over the rows of the block (wca_capture_partials_floats floats in all).
+ * B = ceil(T / 128) token blocks of 4 groups of 32 rows: [L*H][B][4] floats sum_t ||p[t,:]||_2 over the rows of the
+ * group, then [L*H][B][4][F] floats sum_t p[t,f]^2 over the rows of the group (wca_capture_partials_floats floats in
+ * all; groups past the last token row are not written).
  * Only the tcgen05 kernel writes them: wca_capture_writes_partials tells for a launch geometry; passing a
  * non-NULL d_partials when it answers 0 is an error. */
 #define WCA_CAPTURE_RAW_LOGITS 1u

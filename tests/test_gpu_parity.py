@@ -561,8 +561,8 @@ def test_capture_at_baseline_shapes_vs_torch_fp32(cfg, dev):
                                     int(sub["n_tokens"].max()), int(sub["n_frames"].max()), W, 1.0, ws, flags,
                                     partials if name == "tc" else None)
         outs[name] = ws
-    # scores finished from the partials == scores computed by reading the maps (every partial slot was written: no NaN left)
-    assert not torch.isnan(partials).any()
+    # scores finished from the partials == scores computed by reading the maps (a slot the kernel failed to write would
+    # leave its NaN in the score; slots of row groups past the last token are never read)
     d_all = _cabi.upload_utts(recs, dev)
     for w_col, w_row in ((1.0, 1.0), (0.5, 2.0), (0.0, 1.0)):
         s_read = torch.empty(B * L * H, device=dev)

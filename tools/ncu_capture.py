@@ -33,11 +33,19 @@ for b in range(B):
     buckets.setdefault(1 if simt else _cluster_bucket(int(Fs[b])), []).append(b)
 launches = [(recs[m], _cabi.upload_utts(recs[m], dev)) for _, m in sorted(buckets.items())]
 ws = torch.empty(off, device=dev)
+partials = None
+if os.environ.get("WCA_PARTIALS", "0") == "1" and not simt:  # head-score partials written by the score warps
+    poff = 0
+    for b in range(B):
+        recs[b]["part_off"] = poff
+        poff += _cabi.capture_partials_floats(L * H, int(Ts[b]), int(Fs[b]))
+    partials = torch.empty(poff, device=dev)
+    launches = [(recs[m], _cabi.upload_utts(recs[m], dev)) for _, m in sorted(buckets.items())]
 
 def capture():
     for sub, d in launches:
         _cabi.capture_attention(q, k, H, H * D, H * D, d, len(sub), int(sub["n_tokens"].max()), int(sub["n_frames"].max()),
-                                3, 1.0, ws, flags)
+                                3, 1.0, ws, flags, partials)
 
 bytes_alg = 4 * off + sum(4 * L * (int(t) + int(f)) * H * D for t, f in zip(Ts, Fs))
 for _ in range(10):
@@ -54,5 +62,5 @@ for _ in range(reps):
     b_.record(); torch.cuda.synchronize()
     times.append(a.elapsed_time(b_))
 ms = float(np.median(times))
-print(f"{shape} B={B} {'simt+filter' if simt else 'tcgen05'} dbg={flags:#x}: median {ms:.3f} (min {min(times):.3f}) ms/batch ({len(launches)} launch(es)), algorithmic {bytes_alg/1e6:.1f} MB -> {bytes_alg/ms/1e6:.1f} GB/s "
+print(f"{shape} B={B} {'simt+filter' if simt else 'tcgen05'} dbg={flags:#x} partials={partials is not None}: median {ms:.3f} (min {min(times):.3f}) ms/batch ({len(launches)} launch(es)), algorithmic {bytes_alg/1e6:.1f} MB -> {bytes_alg/ms/1e6:.1f} GB/s "
       f"({bytes_alg/ms/1e6/6548.5*100:.1f}% of measured HBM peak)")

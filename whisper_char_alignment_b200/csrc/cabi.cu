@@ -180,7 +180,7 @@ int wca_capture_writes_partials(int max_frames, int medfilt_width, unsigned flag
 int64_t wca_capture_partials_floats(int n_heads, int n_tokens, int n_frames) {
     if (n_heads <= 0 || n_tokens <= 0 || n_frames <= 0) return 0;
     const int64_t token_blocks = (n_tokens + 127) / 128;
-    return (int64_t)n_heads * token_blocks * (1 + (int64_t)n_frames);
+    return (int64_t)n_heads * token_blocks * 4 * (1 + (int64_t)n_frames);
 }
 
 int wca_head_scores_from_partials(const float *d_partials, const wca_utt_t *d_utts, int n_utts, int n_heads, float w_colnorm,

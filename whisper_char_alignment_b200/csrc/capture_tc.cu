@@ -73,9 +73,7 @@ constexpr int kOffKHi = kOffQLo + kQBytes;
 constexpr int kOffKLo = kOffKHi + kKBytes;
 constexpr int kOffTile = kOffKLo + kKBytes;                     // 8 epilogue warps x 32 x 17 floats
 constexpr int kOffStat = kOffTile + 8 * 32 * kTilePitch * 4;    // [group][tile parity][128] x {m, sum, sum of squares, -}
-constexpr int kOffColSs = kOffStat + 2 * 2 * kRows * 16;        // [group][epilogue warp][224]: column sums of squares of a tile
-constexpr int kOffRed = kOffColSs + 2 * 4 * kMaxOwn * 4;        // [group][4] warp partials of the tile reductions
-constexpr int kOffBar = kOffRed + 2 * 4 * 4;
+constexpr int kOffBar = kOffStat + 2 * 2 * kRows * 16;
 enum Bar {
     kKFull = 0,                  // TMA -> splitters (transaction bytes): K slab landed
     kQFull = kKFull + 1,         // ... Q tile landed
@@ -136,8 +134,8 @@ struct Geo {
     int layer, col0;         // decoder layer and first float column of the head
     int qrow0, krow0;        // first Q row of the tile / first K row of the utterance
     float *out;              // row 0 of this tile, frame 0
-    float *row_part;         // head-score partials of this tile: sum_t ||p[t,:]||_2 over its token rows (one float) ...
-    float *col_ss;           // ... and sum_t p[t,f]^2 over its token rows, frame 0 (F floats); nullptr: not wanted
+    float *row_part;         // head-score partials of this tile, per group of 32 token rows: sum_t ||p[t,:]||_2 (4 floats) ...
+    float *col_ss;           // ... and sum_t p[t,f]^2, frame 0 ([4][F] floats); nullptr: not wanted
 };
 
 template <int W>
@@ -159,11 +157,12 @@ __device__ __forceinline__ Geo decode_tile(const KernelArgs &a, int tile, uint32
     g.out = a.ws + u.ws_off + ((int64_t)lh * g.T + t0) * g.F;
     g.row_part = g.col_ss = nullptr;
     if (a.partials != nullptr && !a.raw_logits) {
-        // per utterance: [lh][token block] row terms, then [lh][token block][F] column sums of squares
+        // per utterance: [lh][token block][4 row groups] row terms, then [lh][token block][4 row groups][F] column sums
+        // of squares: every epilogue warp writes the partials of its own 32 token rows, nothing is combined in the kernel
         const int tbu = (g.T + kRows - 1) / kRows;
         float *base = a.partials + u.part_off;
-        g.row_part = base + (int64_t)lh * tbu + tb;
-        g.col_ss = base + (int64_t)a.lh_count * tbu + ((int64_t)lh * tbu + tb) * g.F;
+        g.row_part = base + ((int64_t)lh * tbu + tb) * 4;
+        g.col_ss = base + (int64_t)a.lh_count * tbu * 4 + ((int64_t)lh * tbu + tb) * 4 * g.F;
     }
     const int slab = (((g.F + (int)csize - 1) / (int)csize) + 15) & ~15;
     g.f0 = (int)crank * slab;
@@ -258,7 +257,7 @@ struct RowStats {
 template <int W>
 __device__ __forceinline__ void filter_exp_block(uint32_t trow, int b, int b_lo, int n_blocks, int tail, bool filter,
                                                  float scale2, float (&ptail)[Tail<W>::kLen], float (&cur)[16],
-                                                 float (&next)[16], RowStats &st) {
+                                                 float (&next)[16], RowStats &st, bool want_ss) {
     float med[16];
     median_block<W>(ptail, cur, next, med);
     if (W > 1 && !filter) {  // rows of at most W/2 frames are not filtered (as upstream): rare, kept off the hot path
@@ -317,7 +316,7 @@ __device__ __forceinline__ void filter_exp_block(uint32_t trow, int b, int b_lo,
     }
     st.row_sum += ((med[0] + med[1]) + (med[2] + med[3])) + ((med[4] + med[5]) + (med[6] + med[7])) +
                   (((med[8] + med[9]) + (med[10] + med[11])) + ((med[12] + med[13]) + (med[14] + med[15])));
-    {
+    if (want_ss) {
         // sum of squares of the row (head scores, timing.py:24: ||a[t,:]||_2 = sqrt(sum e^2) / sum e); two chains
         float q0 = med[0] * med[0], q1 = med[1] * med[1];
 #pragma unroll
@@ -353,7 +352,6 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
     const uint32_t trow = acc + ((uint32_t)(ewarp * 32) << 16) + kOwnCol0;  // own frame 0 of this lane quarter
     const int tail = g.n_own - 16 * (n_blocks - 1);  // valid columns of the last block (1..16)
     float4 *sstat = reinterpret_cast<float4 *>(smem + kOffStat) + grp * 2 * kRows;  // [tile parity][128] x {m, sum, ss, -}
-    float row_term = 0.f;  // ||p[row,:]||_2 of the full row, in the one thread that reports it (head scores)
     const uint32_t bar_xmax = smem_u32(smem + kOffBar) + 8u * (kXMax + grp);
 
     float inv_sum = a.s;  // raw-logit mode: only the 2^-3 of the operand scaling is applied
@@ -374,6 +372,7 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
         // memory instead of two and a single exchange of (m, sum) pairs between column halves / cluster ranks.
         const float kLog2e = 1.4426950408889634f;
         const float scale2 = a.qk_scale * kLog2e;
+        const bool want_ss = g.row_part != nullptr && !(a.dbg & 0x400u);  // (0x400: experiment switch)
         RowStats st{-INFINITY, 0.f, 0.f};
         if (sweep) {
             float ptail[Tail<W>::kLen], bufa[16], bufb[16];
@@ -390,9 +389,9 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
             }
 #pragma unroll 1
             for (int b = b_lo; b < b_hi; b += 2) {
-                filter_exp_block<W>(trow, b, b_lo, n_blocks, tail, g.half > 0, scale2, ptail, bufa, bufb, st);
+                filter_exp_block<W>(trow, b, b_lo, n_blocks, tail, g.half > 0, scale2, ptail, bufa, bufb, st, want_ss);
                 if (b + 1 < b_hi)
-                    filter_exp_block<W>(trow, b + 1, b_lo, n_blocks, tail, g.half > 0, scale2, ptail, bufb, bufa, st);
+                    filter_exp_block<W>(trow, b + 1, b_lo, n_blocks, tail, g.half > 0, scale2, ptail, bufb, bufa, st, want_ss);
             }
             tmem_wait_st();
         }
@@ -440,9 +439,12 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
                     gss += pr[r].z * (f * f);
                 }
         }
-        // exactly one thread per token row reports the row norm: rank 0 of a cluster, the first copy of a mirrored row
-        if (g.row_part != nullptr && row_ok && (csize == 1 || cluster_ctarank() == 0) && (!g.dup || ewarp < 2))
-            row_term = sqrtf(gss) / gsum;
+        // head scores, row term of this warp's 32 token rows (timing.py:24): one thread per row reports -- rank 0 of a
+        // cluster, the first copy of a mirrored row -- and a fixed shuffle tree adds them (deterministic)
+        if (g.row_part != nullptr && rows_live && (csize == 1 || cluster_ctarank() == 0) && (!g.dup || ewarp < 2)) {
+            const float term = warp_sum(row_ok ? sqrtf(gss) / gsum : 0.f);
+            if (lane == 0) g.row_part[lw] = term;
+        }
         inv_sum = (m2 > -INFINITY ? ex2_approx(m2 - gmax) : 0.f) / gsum;  // this thread's e values are relative to its own m
         // lanes past the last token row hold finite values nobody stores; as exact zeros in the transposition tile they also
         // drop out of the column sums of the head scores without a per-element predicate
@@ -450,10 +452,8 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
         stamp(tr, seq, kEvEpiXSum);
     }
 
-    // column partials of this warp's rows for the head scores: [group][epilogue warp][own frame]
-    float *colss = g.col_ss != nullptr ? reinterpret_cast<float *>(smem + kOffColSs) + (grp * 4 + ewarp) * kMaxOwn : nullptr;
-    if (colss != nullptr && !g.dup && csize == 1)
-        named_bar_sync(1 + grp, kEpiThreads);  // nobody still sums the previous tile's partials (see the end of this function)
+    // column partials of this warp's 32 token rows for the head scores, written straight to the partial buffer
+    float *colss = (g.col_ss != nullptr && !(a.dbg & 0x200u)) ? g.col_ss + (int64_t)lw * g.F + g.f0 : nullptr;  // (0x200: experiment switch)
     // sweep C: normalise, transpose 32x16 blocks through shared memory, coalesced row stores.
     // Lane (c, rsel) stores column c of rows rsel, rsel+2, ...: two 64-byte row segments per
     // instruction, the address advancing by two rows per step.
@@ -516,34 +516,13 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
                 }
                 float q = q0 + q1;
                 q += __shfl_xor_sync(0xffffffffu, q, 16);
-                if (lane < 16) colss[16 * b + lane] = q;
+                if (lane < 16 && g.f0 + 16 * b + lane < g.f1) colss[16 * b + lane] = q;  // 64 contiguous bytes per block
             }
             __syncwarp();
             tmem_ld_wait(v);
         }
     }
     stamp(tr, seq, kEvEpiC);
-    if (g.col_ss != nullptr) {
-        // ---- head-score partials of the tile (replaces a second full read of the maps by wca_head_scores) ----
-        // row term: fixed shuffle tree per warp, warps added in order by one thread (deterministic)
-        float *red = reinterpret_cast<float *>(smem + kOffRed) + grp * 4;
-        const float wsum = warp_sum(row_term);
-        if (lane == 0) red[ewarp] = wsum;
-        named_bar_sync(1 + grp, kEpiThreads);  // column partials and warp sums of all four warps are in shared memory
-        const int t = ewarp * 32 + lane;
-        if (t == 0 && (csize == 1 || cluster_ctarank() == 0)) *g.row_part = ((red[0] + red[1]) + red[2]) + red[3];
-        const float *cs = reinterpret_cast<const float *>(smem + kOffColSs) + grp * 4 * kMaxOwn;
-        const int live_warps = min(g.dup ? 2 : 4, (g.rows_valid + 31) >> 5);  // logical 32-row groups with token rows
-        for (int col = t; col < g.n_own; col += kEpiThreads) {
-            // mirrored tiles: warps 0/1 swept the first `split` blocks of the row groups 0/1, warps 2/3 the rest
-            const int w0 = (g.dup && (col >> 4) >= split) ? 2 : 0;
-            float acc = 0.f;
-            for (int w = 0; w < live_warps; ++w) acc += cs[(w0 + w) * kMaxOwn + col];  // fixed order
-            g.col_ss[g.f0 + col] = acc;
-        }
-        // the partials are overwritten by the group's next tile in ITS store sweep, which sits behind that tile's
-        // statistics-exchange barrier (mirrored and cluster tiles) or behind the barrier plain tiles take before the sweep
-    }
     return released;
 }
 

@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(256) head_scores_kernel(const float *__restric
 }
 
 // Head scores from the partials the capture kernel leaves behind (wca_capture_attention with d_partials): per
-// (utterance, head, block of 128 tokens) the row term sum_t ||p[t,:]||_2 and the F column sums of squares.  One warp
-// per (utterance, head): sum_f sqrt(sum over token blocks) in a fixed order -- no second read of the maps.
+// (utterance, head, block of 128 tokens, group of 32 token rows) the row term sum_t ||p[t,:]||_2 and the F column sums of
+// squares.  One warp per (utterance, head): sum_f sqrt(sum over row groups) in a fixed order -- no second read of the maps.
 // grid (ceil(n_heads / 4), n_utts), block 128.
 __global__ void __launch_bounds__(128) scores_from_partials_kernel(const float *__restrict__ partials,
                                                                    const wca_utt_t *__restrict__ utts, int n_heads,
@@ -137,14 +137,15 @@ __global__ void __launch_bounds__(128) scores_from_partials_kernel(const float *
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int head = blockIdx.x * 4 + warp;
     if (head >= n_heads) return;
-    const int F = u.n_frames, tbu = (u.n_tokens + 127) / 128;
-    const float *row_part = partials + u.part_off + (int64_t)head * tbu;
-    const float *col_ss = partials + u.part_off + (int64_t)n_heads * tbu + (int64_t)head * tbu * F;
+    const int T = u.n_tokens, F = u.n_frames, tbu = (T + 127) / 128;
+    const int groups = (T + 31) / 32;  // groups of 32 token rows that exist: group g lives in token block g / 4, slot g % 4
+    const float *row_part = partials + u.part_off + (int64_t)head * tbu * 4;
+    const float *col_ss = partials + u.part_off + (int64_t)n_heads * tbu * 4 + (int64_t)head * tbu * 4 * F;
     float col = 0.f;
     if (w_col > 0.f)
         for (int f = lane; f < F; f += kWarp) {
             float ss = 0.f;
-            for (int tb = 0; tb < tbu; ++tb) ss += col_ss[(int64_t)tb * F + f];
+            for (int g = 0; g < groups; ++g) ss += col_ss[(int64_t)g * F + f];  // slots of one head are contiguous: [tb][4][F]
             col += sqrtf(ss);
         }
     col = warp_sum(col);
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(128) scores_from_partials_kernel(const float *
         if (w_col > 0.f) score += w_col * col;
         if (w_row > 0.f) {
             float row = 0.f;
-            for (int tb = 0; tb < tbu; ++tb) row += row_part[tb];
+            for (int g = 0; g < groups; ++g) row += row_part[g];
             score += w_row * row;
         }
         scores[u.score_off + head] = score;
