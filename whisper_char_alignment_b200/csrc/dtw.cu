@@ -533,22 +533,28 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_multi_kernel(const DtwLaun
     }
 }
 
-// ---- long problems: lanes own strips of 16 FRAMES and sweep DOWN the text rows --------------------------------
+// ---- long problems: lanes own strips of 8 FRAMES and sweep DOWN the text rows --------------------------------
 // The row-strip kernels above read the cost matrix against its layout (one 4-byte load per lane and text row, 32
 // cache lines per warp load) and keep that load on the dependency chain; for LibriSpeech-shaped problems (401 x 1500)
 // they ran at ~400 ns per wavefront step.  Here the recurrence is swept the other way round: lane g owns frames
-// 16g .. 16g+15 (94 lanes = 3 warps for 1500 frames) and handles text row i at step s = i + g, so
-//   * a warp reads 2 KB of ONE matrix row per step, contiguous, each lane its own 64 bytes, with cp.async straight into a
+// 8g .. 8g+7 (188 lanes = 6 warps for 1500 frames) and handles text row i at step s = i + g, so
+//   * a warp reads 1 KB of ONE matrix row per step, contiguous, each lane its own 32 bytes, with cp.async straight into a
 //     private ring in shared memory kLongAhead rows ahead (every lane consumes what it loaded itself: no flags, no
 //     barriers, just cp.async.wait_group);
-//   * the sweep has N + lanes - 1 steps (~500) instead of M + lanes - 1 (~1630);
-//   * the trace word of a step is the 16 two-bit codes of the strip: N x lanes 32-bit words in shared memory
-//     (172 KB for the largest legal problem), walked by one thread with bit scans: one dependent shared-memory read
-//     per text row plus one per 16 consecutive time steps.
+//   * the sweep has N + lanes - 1 steps (~590) instead of M + lanes - 1 (~1630), of 8 cells each (a single warp issues one
+//     dependent instruction every ~3 cycles, so the step time is its instruction count: 16 frames per lane and 3 warps
+//     measured 300 us for 401 x 1500, see profiles/r02_dtw_long.md);
+//   * the trace word of a step holds the 8 codes of the strip as two 8-bit masks (bit k: text step, bit 8+k: time
+//     step; neither: diagonal): N x lanes 16-bit words in shared memory (172 KB for the largest legal problem), walked
+//     by one thread with bit scans: one dependent shared-memory read per text row plus one per 8 consecutive time steps;
+//   * a cell is 8 instructions with 3 of them (compare, select, add) on the chain: min(c0, c1) is the only candidate
+//     that can beat the time step, and it can only if c0 and c1 are ordered and different.
 // The cell rule, the fp32 add and therefore every path are those of the other kernels (and of dtw_cpu), bit for bit.
-constexpr int kStripCols = 16;
-constexpr int kLongAhead = 4;               // rows in flight per lane
-constexpr int kLongSlots = kLongAhead + 1;  // ring slots: the row being read is never the one being refilled
+constexpr int kStripCols = 8;
+constexpr int kStripChunks = kStripCols / 4;  // 16-byte pieces of a strip
+constexpr int kLongAhead = 3;               // rows in flight per lane
+constexpr int kLongSlots = kLongAhead + 1;  // ring slots (a power of two): the row being read is never the one being refilled
+static_assert((kLongSlots & (kLongSlots - 1)) == 0, "slot index is a mask");
 
 __device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gmem_src, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
@@ -572,13 +578,13 @@ static LongPlan dtw_long_plan(int max_rows, int max_frames) {
     const size_t lanes = 32 * (size_t)l.wpp;
     l.jump = (size_t)((max_rows + 3) & ~3) * 4;
     l.edge = ((size_t)(l.wpp - 1) * (size_t)max_rows * 8 + 15) & ~(size_t)15;
-    l.ring = (size_t)kLongSlots * 4 * lanes * 16;
-    l.trace = (size_t)max_rows * lanes * 4;
+    l.ring = (size_t)kLongSlots * kStripChunks * lanes * 16;
+    l.trace = ((size_t)max_rows * lanes * 2 + 15) & ~(size_t)15;
     l.smem = l.jump + l.edge + l.ring + l.trace;
     return l;
 }
 
-template <int WPP>
+template <int WPP, bool kFlip>
 __global__ void __launch_bounds__(32 * WPP) dtw_align_long_kernel(const DtwLaunch p, int max_rows) {
     constexpr int L = 32 * WPP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -587,13 +593,13 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_long_kernel(const DtwLaunc
     const wca_utt_t u = p.utts[prob];
     const int N = u.row_end - u.row_begin;
     const int M = u.n_frames;
-    // shared memory: [jump frames][edge words (WPP-1) x max_rows][cost ring kLongSlots x 4 x L float4][trace N x L words]
+    // shared memory: [jump frames][edge words (WPP-1) x max_rows][cost ring kLongSlots x 2 x L float4][trace N x L 16-bit words]
     int32_t *jump_s = reinterpret_cast<int32_t *>(smem_raw);
     const size_t jump_bytes = (size_t)((max_rows + 3) & ~3) * 4;
     const size_t edge_bytes = ((size_t)(WPP - 1) * max_rows * 8 + 15) & ~(size_t)15;
     unsigned long long *edge = reinterpret_cast<unsigned long long *>(smem_raw + jump_bytes);
     float4 *ring = reinterpret_cast<float4 *>(smem_raw + jump_bytes + edge_bytes);
-    uint32_t *trace = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(ring) + (size_t)kLongSlots * 4 * L * 16);
+    uint16_t *trace = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(ring) + (size_t)kLongSlots * kStripChunks * L * 16);
     if (N <= 0 || M <= 0) {
         if (g == 0 && p.path_len) p.path_len[prob] = 0;
         return;
@@ -605,17 +611,16 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_long_kernel(const DtwLaunc
     const float *xg = p.matrix + u.matrix_off;
     const int j0 = g * kStripCols;                       // first frame of the strip
     const int n_cols = max(0, min(kStripCols, M - j0));  // frames of the strip inside the matrix
-    const bool flip = p.negate != 0;
     // every matrix row starts 16-byte aligned (base aligned, M % 4 == 0): 16-byte copies; else 4-byte copies
     const bool vec = (reinterpret_cast<uintptr_t>(xg) & 15) == 0 && (M & 3) == 0;
     // ring slot of row i: i % kLongSlots; chunk q of the strip at ring[(slot * 4 + q) * L + g] (conflict-free 16-byte reads)
     auto prefetch = [&](int i) {
         if (i >= 0 && i < N && n_cols > 0) {
             const float *src = xg + (int64_t)i * M + j0;
-            float4 *dst = ring + (size_t)((i % kLongSlots) * 4) * L + g;
+            float4 *dst = ring + (size_t)((i & (kLongSlots - 1)) * kStripChunks) * L + g;
             if (vec) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < kStripChunks; ++q) {
                     const int valid = max(0, min(4, n_cols - 4 * q));
                     cp_async16_zfill(dst + q * L, valid > 0 ? src + 4 * q : xg, 4 * valid);  // bytes past `valid` are zero-filled
                 }
@@ -663,34 +668,36 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_long_kernel(const DtwLaunc
         cp_async_wait<kLongAhead - 1>();  // this lane's copy of row i has landed
         float x[kStripCols];
         {
-            const float4 *slot = ring + (size_t)((act ? i % kLongSlots : 0) * 4) * L + g;
+            const float4 *slot = ring + (size_t)((i & (kLongSlots - 1)) * kStripChunks) * L + g;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < kStripChunks; ++q) {
                 const float4 v = act ? slot[q * L] : make_float4(0.f, 0.f, 0.f, 0.f);
                 x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
             }
         }
         prefetch(i + kLongAhead);  // into the slot read one step ago, never the one just read
-        uint32_t tw = 0;
+        uint32_t tw_text = 0, tw_time = 0;  // bit k: the cell of frame j0 + k takes the text step / the time step
         float c0 = diag_in;   // cost[i-1][j-1]
         float c2 = left_in;   // cost[i][j-1]
 #pragma unroll
         for (int k = 0; k < kStripCols; ++k) {
             const float c1 = up[k];  // cost[i-1][j]
             // dtw_cpu's rule: the diagonal only if strictly below both others, then the text step only if strictly below
-            // both others, else the time step (ties and NaN).  The part that does not involve c2 is off the chain.
-            const bool lt01 = c0 < c1, lt10 = c1 < c0;
-            const float a = lt01 ? c0 : c1;           // the only candidate that can beat c2
-            const bool win = (lt01 | lt10) & (a < c2);
+            // both others, else the time step (ties and NaN).  Only min(c0, c1) can beat c2, and only when c0 and c1 are
+            // ordered and different; everything but (compare with c2, select, add) is off the chain.
+            const bool ordered_ne = (c0 < c1) || (c0 > c1);
+            const float a = fminf(c0, c1);
+            const bool win = ordered_ne && (a < c2);
+            const bool text = win && (c1 < c0);
             const float cm = win ? a : c2;
-            const uint32_t code = win ? (lt01 ? 0u : 1u) : 2u;
-            tw |= code << (2 * k);
-            const float xv = flip ? -x[k] : x[k];
-            const float cost = __fadd_rn(xv, cm);
+            tw_time |= win ? 0u : (1u << k);
+            tw_text |= text ? (1u << k) : 0u;
+            const float cost = kFlip ? __fsub_rn(cm, x[k]) : __fadd_rn(x[k], cm);  // (-x) + cm, bit for bit
             c0 = c1;       // this column's old value is the next column's diagonal
             c2 = cost;     // this column's new value is the next column's left
             up[k] = cost;
         }
+        const uint16_t tw = (uint16_t)(tw_text | (tw_time << kStripCols));
         diag_in = left_in;
         last_new = c2;
         if (act) {
@@ -707,23 +714,23 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_long_kernel(const DtwLaunc
         if (!p.path_text) {
             int row = N - 1, col = M - 1, n_diag = 0;
             while (row >= 0 && col >= 0) {
-                int wi = col >> 4;
-                const int kc = col & 15;
+                int wi = col / kStripCols;
+                const int kc = col % kStripCols;
                 uint32_t w = trace[(size_t)row * L + wi];
-                uint32_t leave = ~w & 0xAAAAAAAAu;                      // bit 2k+1 set where code k is 0 or 1
-                if (kc < 15) leave &= (1u << (2 * kc + 2)) - 1u;        // cells at or left of the current frame
+                uint32_t leave = ~(w >> kStripCols) & 0xFFu;            // bit k set where cell k leaves the row (not a time step)
+                leave &= (2u << kc) - 1u;                               // cells at or left of the current frame
                 while (leave == 0u && wi > 0) {
                     --wi;
                     w = trace[(size_t)row * L + wi];
-                    leave = ~w & 0xAAAAAAAAu;
+                    leave = ~(w >> kStripCols) & 0xFFu;
                 }
                 if (leave == 0u) break;  // left border: the remaining rows keep -1 (upstream's index arithmetic gives frame -1)
-                const int k = (31 - __clz(leave)) >> 1;
-                const uint32_t code = (w >> (2 * k)) & 3u;
+                const int k = 31 - __clz(leave);
+                const bool diag = ((w >> k) & 1u) == 0u;  // leaves the row and is not a text step
                 const int at = wi * kStripCols + k;
                 jump_s[row] = at;       // first path point of the text row
-                n_diag += code == 0u;
-                col = at - (code == 0u);
+                n_diag += diag;
+                col = at - (diag ? 1 : 0);
                 --row;
             }
             if (p.path_len) p.path_len[prob] = N + M - n_diag;  // every diagonal step saves one path point
@@ -738,7 +745,11 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_long_kernel(const DtwLaunc
                 uint32_t code;
                 if (bj == 0) code = 1u;
                 else if (bi == 0) code = 2u;
-                else code = (trace[(size_t)(bi - 1) * L + ((bj - 1) >> 4)] >> (2 * ((bj - 1) & 15))) & 3u;
+                else {
+                    const uint32_t w = trace[(size_t)(bi - 1) * L + (bj - 1) / kStripCols];
+                    const int k = (bj - 1) % kStripCols;
+                    code = ((w >> (kStripCols + k)) & 1u) ? 2u : ((w >> k) & 1u);
+                }
                 if (code != 2u && bi >= 1) jump_s[bi - 1] = bj - 1;
                 if (code == 0u) {
                     --bi;
@@ -845,7 +856,7 @@ static DtwPlan dtw_plan(int max_rows, int max_frames) {
 // next to their trace, as long as its own trace (max_rows x lanes words) fits in shared memory.
 static bool use_long_kernel(int max_rows, int max_frames) {
     const LongPlan lp = dtw_long_plan(max_rows, max_frames);
-    if (lp.wpp > 4 || lp.smem > kSmemBudget) return false;
+    if (lp.wpp > 8 || lp.smem > kSmemBudget) return false;
     return max_rows > 128 || !dtw_plan(max_rows, max_frames).staged;
 }
 
@@ -876,13 +887,17 @@ static int launch_multi(const DtwLaunch &p, size_t smem, cudaStream_t stream) {
     return launch_multi_a<R, WPP, 4>(p, smem, stream);  // 4 columns of lookahead (1..8 measured the same)
 }
 
-template <int WPP>
-static int launch_long(const DtwLaunch &p, int max_rows, size_t smem, cudaStream_t stream) {
+template <int WPP, bool kFlip>
+static int launch_long_f(const DtwLaunch &p, int max_rows, size_t smem, cudaStream_t stream) {
     if (smem > 48u * 1024u)
-        WCA_CUDA(cudaFuncSetAttribute(dtw_align_long_kernel<WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dtw_align_long_kernel<WPP><<<p.n_utts, 32 * WPP, smem, stream>>>(p, max_rows);
+        WCA_CUDA(cudaFuncSetAttribute(dtw_align_long_kernel<WPP, kFlip>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dtw_align_long_kernel<WPP, kFlip><<<p.n_utts, 32 * WPP, smem, stream>>>(p, max_rows);
     WCA_LAUNCH_CHECK("dtw_align_long_kernel");
     return WCA_OK;
+}
+template <int WPP>
+static int launch_long(const DtwLaunch &p, int max_rows, size_t smem, cudaStream_t stream) {
+    return p.negate ? launch_long_f<WPP, true>(p, max_rows, smem, stream) : launch_long_f<WPP, false>(p, max_rows, smem, stream);
 }
 
 template <int R, bool kTraceSmem, bool kStaged>
@@ -937,7 +952,11 @@ int launch_dtw_align(const float *d_matrix, const wca_utt_t *d_utts, int n_utts,
             case 1: return launch_long<1>(p, max_rows, lp.smem, stream);
             case 2: return launch_long<2>(p, max_rows, lp.smem, stream);
             case 3: return launch_long<3>(p, max_rows, lp.smem, stream);
-            default: return launch_long<4>(p, max_rows, lp.smem, stream);
+            case 4: return launch_long<4>(p, max_rows, lp.smem, stream);
+            case 5: return launch_long<5>(p, max_rows, lp.smem, stream);
+            case 6: return launch_long<6>(p, max_rows, lp.smem, stream);
+            case 7: return launch_long<7>(p, max_rows, lp.smem, stream);
+            default: return launch_long<8>(p, max_rows, lp.smem, stream);
         }
     }
     const MultiPlan mp = dtw_multi_plan(max_rows, max_frames);
