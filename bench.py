@@ -302,8 +302,12 @@ def matmul_tflops(dev, tf32: bool, n: int = 8192, reps: int = 6):
 
 def capture_bytes(utts, L, H, d):
     """Algorithmic bytes of the capture launch(es) for a list of utterances:
-    the maps written once, Q and K[:F] read once."""
-    return float(sum(4 * L * H * len(u.tokens) * u.max_frames + 4 * L * (len(u.tokens) + u.max_frames) * d for u in utts))
+    the maps written once, Q and K[:F] read once -- plus the head-score partials the fused epilogue leaves behind
+    (one row term and F column sums of squares per head and group of 32 token rows: ~3 % of the maps), which replace
+    the second full read of the maps that scoring the heads used to cost."""
+    maps = sum(4 * L * H * len(u.tokens) * u.max_frames + 4 * L * (len(u.tokens) + u.max_frames) * d for u in utts)
+    partials = sum(4 * L * H * -(-len(u.tokens) // 32) * (1 + u.max_frames) for u in utts)
+    return float(maps + partials)
 
 
 def main():
@@ -506,7 +510,9 @@ def main():
                          "algorithmic_bytes_per_step": cap_bytes_total / max(args.steps, 1),
                          "launches_per_step": cap_calls / max(args.steps, 1),
                          "ms_per_step": cap_ms / max(args.steps, 1),
-                         "basis": "per step: sum of algorithmic bytes / sum of capture launch time (CUDA events)"},
+                         "basis": "per step: sum of algorithmic bytes / sum of capture launch time (CUDA events)",
+                         "fused": "head-score partials (timing.py:17-34) are produced in the capture epilogue; scoring no longer "
+                                  "reads the maps (see stages_ms_per_step: wca_head_scores_from_partials vs round 1's wca_head_scores)"},
             "roofline_attention": {"kernel": "wca_full_attention (tcgen05, 3 x tf32 split for both contractions)", "bound": "tensor",
                                    "achieved": att_useful, "unit": "TFLOP/s", "executed_tf32": 3.0 * att_useful,
                                    "peak": tf32_tflops, "frac": 3.0 * att_useful / tf32_tflops if tf32_tflops else None,

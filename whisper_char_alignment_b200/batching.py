@@ -5,7 +5,7 @@ Whisper's context: more than 1500 frames (30 s) or more than 448 tokens (infer_a
 utterances go through one forward and one launch per stage, so what shares a batch matters:
 
   * the decoder runs on token rows right-padded to the longest sequence of the batch -> sort by token count;
-  * the capture kernel launches one grid per frame-cluster size (1/2/4/8 CTAs of 224 frames) -> utterances
+  * the capture kernel launches one grid per frame-cluster size (1-6 or 8 CTAs of 224 frames) -> utterances
     of similar duration should share a batch (text length and duration are strongly correlated in speech);
   * the maps of a batch are `4 * L * H * sum(T * F)` bytes and live in HBM at once -> cap them.
 

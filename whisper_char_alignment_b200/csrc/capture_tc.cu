@@ -868,8 +868,10 @@ int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_la
         memcpy(&cache_maps, &maps, sizeof(maps));
         cache_valid = true;
     }
-    int csize = 1;
-    while (csize < 8 && ((((max_frames + csize - 1) / csize) + 15) & ~15) > tc::kMaxOwn) csize *= 2;
+    // CTAs per cluster = 224-frame slabs the longest utterance of the launch needs: 1-6 or 8.  (7 would leave more SMs idle
+    // than 8: clusters do not straddle GPCs, and a GPC of 18 SMs holds two clusters of 7 or of 8, three of 5 or 6, six of 3.)
+    int csize = (max_frames + tc::kMaxOwn - 1) / tc::kMaxOwn;
+    if (csize == 7) csize = 8;
     const int tok_blocks = (max_tokens + tc::kRows - 1) / tc::kRows;
     const int lh_count = n_layers * n_heads;
     const long long tiles = (long long)n_utts * lh_count * tok_blocks;
@@ -918,9 +920,9 @@ int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_la
         WCA_CUDA(cudaFuncSetAttribute(tc::capture_tc_kernel<Wv>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                       tc::kSmemBytes));                                                         \
         if (csize > 1) {                                                                                        \
-            static std::atomic<int> fit_tab[64][4]; /* [device][cluster size 1, 2, 4, 8], zero-initialised */  \
+            static std::atomic<int> fit_tab[64][9]; /* [device][cluster size], zero-initialised */             \
             std::atomic<int> *fit = fit_tab[device & 63];                                                       \
-            const int slot = csize == 2 ? 1 : (csize == 4 ? 2 : 3);                                             \
+            const int slot = csize;                                                                             \
             if (fit[slot] == 0) {                                                                               \
                 int n = 0;                                                                                      \
                 if (cudaOccupancyMaxActiveClusters(&n, tc::capture_tc_kernel<Wv>, &cfg) != cudaSuccess || n < 1) { \

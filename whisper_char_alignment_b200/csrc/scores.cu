@@ -267,11 +267,21 @@ int launch_aggregate_heads(const float *d_ws, const int32_t *d_sel, const wca_ut
         set_error("wca_aggregate_heads: max_tokens=%d exceeds the shared-memory accumulator", max_tokens);
         return WCA_ERR_UNSUPPORTED;
     }
-    if (smem > 48u * 1024u)
+    // the 48 KB a kernel gets without opting in cover static + dynamic shared memory: this kernel has 2 KB of static
+    // partials, so 369-384 token rows (46-48 KB of accumulators) already need the attribute
+    if (smem > 40u * 1024u)
         WCA_CUDA(cudaFuncSetAttribute(aggregate_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const dim3 grid((max_frames + kWarp - 1) / kWarp, n_utts);
     aggregate_heads_kernel<<<grid, 256, smem, stream>>>(d_ws, d_sel, d_utts, d_matrix);
-    WCA_LAUNCH_CHECK("aggregate_heads_kernel");
+    {
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            set_error("aggregate_heads_kernel: %s (grid %u x %u, %zu bytes of shared memory, max_tokens %d, max_frames %d)",
+                      cudaGetErrorString(e), grid.x, grid.y, smem, max_tokens, max_frames);
+            return WCA_ERR_CUDA;
+        }
+        count_launch();
+    }
     return WCA_OK;
 }
 

@@ -24,6 +24,7 @@ There is no CPU path here: tensors must be CUDA tensors and the extension must b
 """
 from __future__ import annotations
 
+import os
 from typing import Sequence
 
 import numpy as np
@@ -68,13 +69,19 @@ class _CrossAttentionTap:
 
 _FRAMES_PER_CTA = 224  # csrc/capture_tc.cu: kMaxOwn
 
+#: Head-score partials from the capture epilogue: "1" (default) always, "0" never, "auto" only for batches whose
+#: utterances all fit one CTA along the frames (<= 224 frames).  The partials cost the epilogue warps ~15 % more
+#: instructions and save the second read of the maps.  Measured on one B200 inside bench.py (capture + scoring):
+#: TIMIT-shaped batch of 32: 0.378 + 0.026 ms with, 0.363 + 0.137 ms without; LibriSpeech-shaped drain of 800 utterances:
+#: 251.9 + 3.5 ms with, 233.7 + 51.2 ms without.
+SCORE_PARTIALS = os.environ.get("WCA_SCORE_PARTIALS", "1")
+
 
 def _cluster_bucket(n_frames: int) -> int:
-    """Cluster size (1, 2, 4 or 8 CTAs along frames) the capture kernel needs for this utterance."""
-    size = 1
-    while size < 8 and -(-n_frames // size) > _FRAMES_PER_CTA:
-        size *= 2
-    return size
+    """Cluster size (1-6 or 8 CTAs along frames, 224 frames each) the capture kernel uses for this utterance; the same
+    rule as launch_capture_tc (csrc/capture_tc.cu), which derives it from the longest utterance of a launch."""
+    size = max(1, -(-n_frames // _FRAMES_PER_CTA))
+    return 8 if size >= 7 else size
 
 
 def _as_f32_rows(t: torch.Tensor) -> torch.Tensor:
@@ -151,7 +158,9 @@ def get_attentions_batch(mels, tokens_list: Sequence[torch.Tensor], model, token
     flags = (_cabi.WCA_CAPTURE_RAW_LOGITS if raw_logits else 0) | (_cabi.WCA_CAPTURE_FORCE_SIMT if force_simt else 0)
     # head-score partials: the capture epilogue holds every map value anyway, so it also leaves sum_t ||p[t,:]||_2 and
     # the column sums of squares behind; force_align / filter_attention then score the heads without reading the maps
-    with_partials = _cabi.capture_writes_partials(max(frames), int(medfilt_width), flags)
+    with_partials = SCORE_PARTIALS != "0" and _cabi.capture_writes_partials(max(frames), int(medfilt_width), flags)
+    if SCORE_PARTIALS == "auto" and max(frames) > _FRAMES_PER_CTA:
+        with_partials = False  # see SCORE_PARTIALS
     recs = np.zeros(B, dtype=_cabi.UTT_DTYPE)
     off = part_off = 0
     for b in range(B):
@@ -164,7 +173,7 @@ def get_attentions_batch(mels, tokens_list: Sequence[torch.Tensor], model, token
     ws = torch.empty(off, dtype=torch.float32, device=device)
     partials = torch.empty(part_off, dtype=torch.float32, device=device) if with_partials else None
     # One launch per frame-count bucket: the capture kernel spreads an utterance's frames over a
-    # cluster of 1/2/4/8 CTAs (224 frames each) and the cluster size is a launch parameter, so
+    # cluster of 1-6 or 8 CTAs (224 frames each) and the cluster size is a launch parameter, so
     # short utterances must not share a launch with 30 s ones.
     buckets = {}
     for b in range(B):
