@@ -107,9 +107,9 @@ def parse():
                     help="extra BASELINE.json configurations measured in the same run ('' = none)")
     ap.add_argument("--libri-utts", type=int, default=N_LIBRISPEECH, help="length of the fixed LibriSpeech-shaped list")
     ap.add_argument("--libri-batch", type=int, default=32, help="largest length-bucketed batch of the LibriSpeech drain")
-    ap.add_argument("--probe-batch", type=int, default=8, help="utterances per probe-sweep step per GPU")
+    ap.add_argument("--probe-batch", type=int, default=32, help="utterances per probe-sweep step per GPU")
     ap.add_argument("--probe-heads", type=int, default=384, help="heads aligned individually per utterance")
-    ap.add_argument("--probe-steps", type=int, default=3)
+    ap.add_argument("--probe-steps", type=int, default=2)
     args = ap.parse_args()
     if args.aggr is None:
         args.aggr = "mean" if args.workload == "ami" else "topk"

@@ -121,8 +121,7 @@ class Attention(nn.Module):
         self._qkv = _FusedWeights()
 
     def _split(self, t):
-        b, n, _ = t.shape
-        return t.view(b, n, self.n_head, -1).transpose(1, 2)
+        return t.unflatten(-1, (self.n_head, -1)).transpose(1, 2)
 
     def forward(self, x, xa=None, causal: bool = False, kv=None, tap=None):
         """kv: (k, v) already projected (views into the decoder's all-layer K/V GEMM); tap: list that receives
@@ -148,9 +147,7 @@ class Attention(nn.Module):
             from . import _cabi
 
             return self.out(_cabi.full_attention(q, k, v, self.n_head)), None
-        if not q.is_contiguous():  # views of a fused projection: head split needs the plain (batch, n, d) layout
-            q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
-        q, k, v = self._split(q), self._split(k), self._split(v)
+        q, k, v = self._split(q), self._split(k), self._split(v)  # views, also of the column slices of a fused projection
         # SDPA's default scale is d_head^-1/2 == (d_head^-1/4)^2, the published scaling
         ctx = F.scaled_dot_product_attention(q, k, v, is_causal=causal and q.shape[2] > 1)
         return self.out(ctx.transpose(1, 2).flatten(2)), None
