@@ -27,10 +27,18 @@ for b in range(B):
     recs[b]["q_row0"], recs[b]["k_row0"], recs[b]["ws_off"] = b * t_max, b * n_ctx, off
     off += L * H * int(Ts[b]) * int(Fs[b])
 d_utts = _cabi.upload_utts(recs, dev)
+partials = None
+if os.environ.get("WCA_PARTIALS", "0") == "1":  # head-score partials produced in the epilogue
+    poff = 0
+    for b in range(B):
+        recs[b]["part_off"] = poff
+        poff += _cabi.capture_partials_floats(L * H, int(Ts[b]), int(Fs[b]))
+    partials = torch.empty(poff, device=dev)
+    d_utts = _cabi.upload_utts(recs, dev)
 ws = torch.empty(off, device=dev)
 for _ in range(2):
-    _cabi.capture_attention(q, k, H, H * D, H * D, d_utts, B, t_max, int(Fs.max()), width, 1.0, ws, 0)
-_cabi.capture_attention(q, k, H, H * D, H * D, d_utts, B, t_max, int(Fs.max()), width, 1.0, ws, _cabi.WCA_CAPTURE_TRACE | dbg)
+    _cabi.capture_attention(q, k, H, H * D, H * D, d_utts, B, t_max, int(Fs.max()), width, 1.0, ws, 0, partials)
+_cabi.capture_attention(q, k, H, H * D, H * D, d_utts, B, t_max, int(Fs.max()), width, 1.0, ws, _cabi.WCA_CAPTURE_TRACE | dbg, partials)
 torch.cuda.synchronize()
 tr = _cabi.capture_trace().reshape(-1, len(EV)).astype(np.float64)
 t0 = tr[tr > 0].min()
