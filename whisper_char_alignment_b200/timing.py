@@ -444,21 +444,87 @@ def probe_heads_batch(ws_list, tokens_list, tokenizer, aligned_unit_type="subwor
     plan = _Plan(ws_list, 0, k)
     _, sel, sel_scores = _score_and_select(plan, w_colnorm, w_rownorm, w_coverage)
     sel_h, score_h = sel.cpu().numpy(), sel_scores.cpu().numpy()
-    heads, toks, tables = [], [], []
+    tables, head_lists = [], []
     for b, w in enumerate(ws_list):
         so = int(plan.recs[b]["sel_off"])
-        table = _score_table(sel_h[so: so + k[b]], score_h[so: so + k[b]], w.shape[1])
-        tables.append(table)
-        flat = w.view(total[b], 1, 1, w.shape[2], w.shape[3])
-        heads.extend(flat[l * w.shape[1] + h] for _, (l, h), _ in table)
-        toks.extend([tokens_list[b]] * len(table))
-    outs = force_align_batch(heads, toks, tokenizer, aligned_unit_type, "mean", 1,
-                             return_matrix=return_matrix) if heads else []
-    res, pos = [], 0
+        tables.append(_score_table(sel_h[so: so + k[b]], score_h[so: so + k[b]], w.shape[1]))
+        head_lists.append(sel_h[so: so + k[b]].astype(np.int64))
+    outs = _align_single_heads(ws_list, head_lists, tokens_list, tokenizer, aligned_unit_type, return_matrix)
+    return [(outs[b], tables[b]) for b in range(B)]
+
+
+def _align_single_heads(ws_list, head_lists, tokens_list, tokenizer, aligned_unit_type, return_matrix):
+    """force_align(w[l, h][None, None], tokens, aggregation="mean", topk=1) for every listed head of every utterance
+    (probe_oracle.py:89-90), as ONE aggregation launch and ONE DTW launch.  The descriptors of the P = sum_b len(head_lists[b])
+    single-head problems are built with numpy from the utterances' base offsets (no per-head tensor views: a sweep of
+    32 utterances is 12 288 problems).  Returns, per utterance, the list of what force_align returns per head."""
+    B = len(ws_list)
+    dev = ws_list[0].device
+    base_ptr = ws_list[0].data_ptr()
+    sot_len = len(tokenizer.sot_sequence)
+    n_heads = np.array([len(h) for h in head_lists], dtype=np.int64)
+    P = int(n_heads.sum())
+    if P == 0:
+        return [[] for _ in range(B)]
+    words_all, wb_all, n_words = [], [], np.zeros(B, dtype=np.int64)
+    for b, toks in enumerate(tokens_list):  # the word grouping is a property of the utterance, not of the head
+        words, word_tokens = split_tokens_on_spaces(list(toks) + [tokenizer.eot], tokenizer, aligned_unit_type)
+        words_all.append((words, word_tokens))
+        n_words[b] = max(len(word_tokens) - 1, 0)
+        wb = np.pad(np.cumsum([len(t) for t in word_tokens[:-1]]), (1, 0)).astype(np.int32)
+        wb_all.append(np.pad(wb, (0, int(n_words[b]) + 1 - len(wb))) if len(wb) < n_words[b] + 1 else wb[: int(n_words[b]) + 1])
+    T = np.array([w.shape[2] for w in ws_list], dtype=np.int64)
+    F = np.array([w.shape[3] for w in ws_list], dtype=np.int64)
+    off = (np.array([w.data_ptr() for w in ws_list], dtype=np.int64) - base_ptr) // 4
+    rep = lambda a: np.repeat(a, n_heads)  # noqa: E731  (per utterance -> per problem)
+    head = np.concatenate(head_lists)
+    row_end = np.maximum(T - 1, sot_len)
+    n_rows = rep(row_end - sot_len)
+
+    def starts(sizes):  # exclusive prefix sum
+        return np.concatenate([[0], np.cumsum(sizes)[:-1]])
+
+    recs = np.zeros(P, dtype=_cabi.UTT_DTYPE)
+    recs["n_tokens"], recs["n_frames"] = rep(T), rep(F)
+    recs["row_begin"], recs["row_end"] = sot_len, rep(row_end)
+    recs["n_sel"], recs["n_words"] = 1, rep(n_words)
+    recs["ws_off"] = rep(off) + head * rep(T * F)  # the block of that head: its list of selected heads is [0]
+    recs["sel_off"] = np.arange(P)
+    recs["matrix_off"] = starts(n_rows * rep(F))
+    recs["path_off"] = starts(n_rows + rep(F))
+    recs["jump_off"] = starts(n_rows)
+    recs["word_off"] = starts(rep(n_words) + 1)
+    d_utts = _cabi.upload_utts(recs, dev)
+    sel = torch.zeros(P, dtype=torch.int32, device=dev)
+    matrix = torch.empty(max(int((n_rows * rep(F)).sum()), 1), dtype=torch.float32, device=dev)
+    max_tokens, max_frames, max_rows = int(T.max()), int(F.max()), int(n_rows.max())
+    _cabi.aggregate_heads(base_ptr, sel, d_utts, P, max_tokens, max_frames, matrix)
+    d_wb = torch.from_numpy(np.concatenate([np.tile(wb_all[b], int(n_heads[b])) for b in range(B)]).astype(np.int32)).to(dev, non_blocking=True)
+    times = torch.empty(2, int((rep(n_words) + 1).sum()), dtype=torch.float64, device=dev)
+    trace_bytes = _cabi.dtw_workspace_bytes(P, max_rows, max_frames)
+    trace_ws = torch.empty(trace_bytes, dtype=torch.uint8, device=dev) if trace_bytes else None
+    _cabi.dtw_align(matrix.data_ptr(), d_utts, P, max_rows, max_frames, True, word_bounds=d_wb, start_times=times[0],
+                    end_times=times[1], trace_ws=trace_ws)
+    matrix_h = matrix.cpu() if return_matrix else None
+    times_h = times.cpu().numpy()
+    out, p = [], 0
+    word_off, matrix_off = recs["word_off"], recs["matrix_off"]
     for b in range(B):
-        res.append((outs[pos: pos + len(tables[b])], tables[b]))
-        pos += len(tables[b])
-    return res
+        words, word_tokens = words_all[b]
+        W, per_head = int(n_words[b]), []
+        for _ in range(int(n_heads[b])):
+            if len(word_tokens) <= 1:
+                per_head.append(_SENTINEL())
+            else:
+                wo = int(word_off[p])
+                m = None
+                if return_matrix:
+                    mo, nr, nf = int(matrix_off[p]), int(n_rows[p]), int(F[b])
+                    m = matrix_h[mo: mo + nr * nf].view(nr, nf)
+                per_head.append((words, times_h[0, wo: wo + W], times_h[1, wo: wo + W], m, None))
+            p += 1
+        out.append(per_head)
+    return out
 
 
 def default_find_alignment(model, tokenizer, text_tokens, mel, max_frames, *, medfilt_width=7, qk_scale=1.0):
