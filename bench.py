@@ -310,6 +310,17 @@ def capture_bytes(utts, L, H, d):
     return float(maps + partials)
 
 
+def pair_roofline(kernel_ms, step_batches, L, H, d, peak):
+    ms = sum(kernel_ms.get(k, (0, 0.0))[1] for k in ("wca_capture_attention", "wca_head_scores", "wca_head_scores_from_partials"))
+    by = float(sum(8 * L * H * len(u.tokens) * u.max_frames + 4 * L * (len(u.tokens) + u.max_frames) * d
+                   for b in step_batches for u in b))
+    gbs = by / (ms / 1000.0) / 1e9 if ms > 0 else 0.0
+    return {"kernels": "wca_capture_attention + wca_head_scores[_from_partials]", "bound": "hbm", "achieved": gbs, "peak": peak,
+            "unit": "GB/s", "frac": gbs / peak, "algorithmic_bytes_per_step": by / max(len(step_batches), 1),
+            "ms_per_step": ms / max(len(step_batches), 1),
+            "basis": "8*L*H*T*F + 4*L*(T+F)*d per utterance (SURVEY.md 8(d): maps written once and read once for scoring)"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -513,6 +524,10 @@ def main():
                          "basis": "per step: sum of algorithmic bytes / sum of capture launch time (CUDA events)",
                          "fused": "head-score partials (timing.py:17-34) are produced in the capture epilogue; scoring no longer "
                                   "reads the maps (see stages_ms_per_step: wca_head_scores_from_partials vs round 1's wca_head_scores)"},
+            # the pair capture + head scoring on SURVEY.md section 8(d)'s figure for it (maps written once by get_attentions
+            # and read once by force_align's scoring, Q / K read once): round 1 ran it as two kernels (0.327 + 0.135 ms for
+            # 1 293 MB = 0.43 of the copy peak), the fused epilogue no longer performs the read at all
+            "roofline_capture_plus_scoring": pair_roofline(kernel_ms, [batches[i] for i in used], L, H, d, peak),
             "roofline_attention": {"kernel": "wca_full_attention (tcgen05, 3 x tf32 split for both contractions)", "bound": "tensor",
                                    "achieved": att_useful, "unit": "TFLOP/s", "executed_tf32": 3.0 * att_useful,
                                    "peak": tf32_tflops, "frac": 3.0 * att_useful / tf32_tflops if tf32_tflops else None,
