@@ -852,16 +852,25 @@ static DtwPlan dtw_plan(int max_rows, int max_frames) {
     return pl;
 }
 
-// The column-strip kernel takes every launch whose problems are long (more than 128 text rows) or too large to stage
-// next to their trace, as long as its own trace (max_rows x lanes words) fits in shared memory.
-static bool use_long_kernel(int max_rows, int max_frames) {
+// The column-strip kernel takes every launch whose problems are long (more than 128 text rows) or too large to stage next to
+// their trace, as long as its own trace (max_rows x lanes words) fits in shared memory -- and also the launches where the staged
+// warp-per-problem kernel would leave the SMs nearly empty or idle behind its shared-memory footprint: a cost matrix that
+// allows fewer than four problems per CTA (probe-shaped 96 x 300: one warp per SM against ten CTAs of two warps; 1 536 problems
+// 693 -> 171 us), or hundreds of problems in flight (1 680 x (41 x 150): 60.8 -> 50.8 us, 6 144: 245 -> 215 us).  A handful of
+// small problems stays with the staged kernel, whose single dependency chain is shorter (16 x (41 x 150): 24 us against 28).
+static bool use_long_kernel(int n_utts, int max_rows, int max_frames) {
     const LongPlan lp = dtw_long_plan(max_rows, max_frames);
     if (lp.wpp > 8 || lp.smem > kSmemBudget) return false;
-    return max_rows > 128 || !dtw_plan(max_rows, max_frames).staged;
+    static const char *force = getenv("WCA_DTW_LONG");  // experiment switch: "1" always, "0" never (when the other kernels can)
+    if (force && force[0] == '1') return true;
+    if (force && force[0] == '0' && max_rows <= 1024) return false;
+    if (max_rows > 128) return true;
+    const DtwPlan pl = dtw_plan(max_rows, max_frames);
+    return !pl.staged || pl.warps < 4 || n_utts >= 512;
 }
 
 int64_t dtw_workspace_bytes(int n_utts, int max_rows, int max_frames) {
-    if (use_long_kernel(max_rows, max_frames)) return 0;
+    if (use_long_kernel(n_utts, max_rows, max_frames)) return 0;
     const MultiPlan m = dtw_multi_plan(max_rows, max_frames);
     if (m.wpp && n_utts <= 48) return m.trace_in_smem ? 0 : (int64_t)n_utts * (int64_t)m.trace;  // same rule as the launch
     if (dtw_plan(max_rows, max_frames).trace_in_smem) return 0;
@@ -941,7 +950,7 @@ int launch_dtw_align(const float *d_matrix, const wca_utt_t *d_utts, int n_utts,
     p.end_times = d_end_times;
     p.trace_ws = nullptr;
     p.jump_stride = (max_rows + 3) & ~3;
-    if (use_long_kernel(max_rows, max_frames)) {
+    if (use_long_kernel(n_utts, max_rows, max_frames)) {
         const LongPlan lp = dtw_long_plan(max_rows, max_frames);
         p.trace_stride = (int64_t)lp.trace;
         p.trace_in_smem = 1;
