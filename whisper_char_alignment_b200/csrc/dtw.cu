@@ -578,7 +578,7 @@ static LongPlan dtw_long_plan(int max_rows, int max_frames) {
     const size_t lanes = 32 * (size_t)l.wpp;
     l.jump = (size_t)((max_rows + 3) & ~3) * 4;
     l.edge = ((size_t)(l.wpp - 1) * (size_t)max_rows * 8 + 15) & ~(size_t)15;
-    l.ring = (size_t)kLongSlots * kStripChunks * lanes * 16;
+    l.ring = (size_t)kLongSlots * kStripChunks * lanes * 16 + (size_t)kStripChunks * 16;  // + one zeroed chunk
     l.trace = ((size_t)max_rows * lanes * 2 + 15) & ~(size_t)15;
     l.smem = l.jump + l.edge + l.ring + l.trace;
     return l;
@@ -599,7 +599,8 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_long_kernel(const DtwLaunc
     const size_t edge_bytes = ((size_t)(WPP - 1) * max_rows * 8 + 15) & ~(size_t)15;
     unsigned long long *edge = reinterpret_cast<unsigned long long *>(smem_raw + jump_bytes);
     float4 *ring = reinterpret_cast<float4 *>(smem_raw + jump_bytes + edge_bytes);
-    uint16_t *trace = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(ring) + (size_t)kLongSlots * kStripChunks * L * 16);
+    uint16_t *trace = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(ring) + (size_t)kLongSlots * kStripChunks * L * 16 +
+                                                   (size_t)kStripChunks * 16);
     if (N <= 0 || M <= 0) {
         if (g == 0 && p.path_len) p.path_len[prob] = 0;
         return;
@@ -613,21 +614,29 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_long_kernel(const DtwLaunc
     const int n_cols = max(0, min(kStripCols, M - j0));  // frames of the strip inside the matrix
     // every matrix row starts 16-byte aligned (base aligned, M % 4 == 0): 16-byte copies; else 4-byte copies
     const bool vec = (reinterpret_cast<uintptr_t>(xg) & 15) == 0 && (M & 3) == 0;
-    // ring slot of row i: i % kLongSlots; chunk q of the strip at ring[(slot * 4 + q) * L + g] (conflict-free 16-byte reads)
-    auto prefetch = [&](int i) {
-        if (i >= 0 && i < N && n_cols > 0) {
-            const float *src = xg + (int64_t)i * M + j0;
-            float4 *dst = ring + (size_t)((i & (kLongSlots - 1)) * kStripChunks) * L + g;
+    // Ring slot of row r: r % kLongSlots; chunk q of the strip at ring[(slot * kStripChunks + q) * L + g] (conflict-free
+    // 16-byte reads).  Everything that does not change from step to step is hoisted: the bytes of each chunk that lie inside
+    // the matrix (the rest of a copy is zero-filled), the lane's column of the ring, running offsets instead of products.
+    int chunk_bytes[kStripChunks];
+#pragma unroll
+    for (int q = 0; q < kStripChunks; ++q) chunk_bytes[q] = 4 * max(0, min(4, n_cols - 4 * q));
+    float4 *ring_lane = ring + g;
+    const float4 *zero4 = ring + (size_t)kLongSlots * kStripChunks * L;  // one zeroed chunk: what lanes outside the matrix read
+    if (g < kStripChunks) ring[(size_t)kLongSlots * kStripChunks * L + g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    auto prefetch = [&](int r, int64_t row_off) {  // row r of the matrix (at float offset row_off + j0) into its ring slot
+        if ((unsigned)r < (unsigned)N && n_cols > 0) {
+            const float *src = xg + row_off + j0;
+            float4 *dst = ring_lane + (r & (kLongSlots - 1)) * (kStripChunks * L);
             if (vec) {
 #pragma unroll
-                for (int q = 0; q < kStripChunks; ++q) {
-                    const int valid = max(0, min(4, n_cols - 4 * q));
-                    cp_async16_zfill(dst + q * L, valid > 0 ? src + 4 * q : xg, 4 * valid);  // bytes past `valid` are zero-filled
-                }
+                for (int q = 0; q < kStripChunks; ++q)
+                    if (chunk_bytes[q] > 0) cp_async16_zfill(dst + q * L, src + 4 * q, chunk_bytes[q]);
             } else {
 #pragma unroll
                 for (int k = 0; k < kStripCols; ++k)
-                    cp_async4_zfill(reinterpret_cast<float *>(dst + (k >> 2) * L) + (k & 3), k < n_cols ? src + k : xg, k < n_cols ? 4 : 0);
+                    if (k < n_cols) cp_async4_zfill(reinterpret_cast<float *>(dst + (k >> 2) * L) + (k & 3), src + k, 4);
+                    else reinterpret_cast<float *>(dst + (k >> 2) * L)[k & 3] = 0.f;
             }
         }
         cp_async_commit();
@@ -638,44 +647,45 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_long_kernel(const DtwLaunc
     float up[kStripCols];
 #pragma unroll
     for (int k = 0; k < kStripCols; ++k) up[k] = INFINITY;
-    float last_new = INFINITY;                      // cost[i][j0 + 15] of the row just finished (what the right neighbour needs)
+    float last_new = INFINITY;                      // cost[i][j0 + 7] of the row just finished (what the right neighbour needs)
     float diag_in = (g == 0) ? 0.f : INFINITY;      // cost[i-1][j0 - 1]: table cell (0, 0) = 0 for the first strip's first row
     const volatile unsigned long long *edge_in = edge + (size_t)(warp > 0 ? warp - 1 : 0) * N;
     volatile unsigned long long *edge_out = edge + (size_t)(warp < WPP - 1 ? warp : 0) * N;
     const bool warp_live = warp * 32 * kStripCols < M;  // warps whose strips all lie past the last frame only idle along
+    const bool polls = lane == 0 && warp > 0, publishes = lane == 31 && warp < WPP - 1;
 
     // copy group n of a lane carries its row n - g: kLongAhead groups before the loop, one more per step
 #pragma unroll
-    for (int a = 0; a < kLongAhead; ++a) prefetch(a - g);
+    for (int a = 0; a < kLongAhead; ++a) prefetch(a - g, (int64_t)(a - g) * M);
     const int n_steps = N + L - 1;
+    int i = -g;                                          // text row of this lane at this step
+    int64_t ahead_off = (int64_t)(kLongAhead - g) * M;   // float offset of row i + kLongAhead
+    int trace_off = -g * L + g;                          // trace[i * L + g]
     if (warp_live)
-    for (int s = 0; s < n_steps; ++s) {
-        const int i = s - g;  // text row of this lane at this step
+    for (int s = 0; s < n_steps; ++s, ++i, ahead_off += M, trace_off += L) {
         const bool act = (unsigned)i < (unsigned)N;
         // left neighbour's newest last cell = cost[i][j0 - 1]
         float left_in = __shfl_up_sync(0xffffffffu, last_new, 1);
-        if (lane == 0) {
-            left_in = INFINITY;  // table column 0
-            if (warp > 0 && act) {
-                unsigned long long w = edge_in[i];
-                for (uint32_t spins = 0; (uint32_t)(w >> 32) != (uint32_t)(i + 1); ++spins) {
-                    if (spins > (1u << 26)) __trap();  // a protocol bug must surface as a launch failure, not a hung GPU
-                    w = edge_in[i];
-                }
-                left_in = __uint_as_float((uint32_t)w);
+        if (lane == 0) left_in = INFINITY;  // table column 0 (first warp); the next warps take it from the hand-over word
+        if (polls && act) {
+            unsigned long long w = edge_in[i];
+            for (uint32_t spins = 0; (uint32_t)(w >> 32) != (uint32_t)(i + 1); ++spins) {
+                if (spins > (1u << 26)) __trap();  // a protocol bug must surface as a launch failure, not a hung GPU
+                w = edge_in[i];
             }
+            left_in = __uint_as_float((uint32_t)w);
         }
         cp_async_wait<kLongAhead - 1>();  // this lane's copy of row i has landed
         float x[kStripCols];
         {
-            const float4 *slot = ring + (size_t)((i & (kLongSlots - 1)) * kStripChunks) * L + g;
+            const float4 *slot = ring_lane + (i & (kLongSlots - 1)) * (kStripChunks * L);
 #pragma unroll
             for (int q = 0; q < kStripChunks; ++q) {
-                const float4 v = act ? slot[q * L] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 v = *(act ? slot + q * L : zero4);  // one select on the address instead of four on the values
                 x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
             }
         }
-        prefetch(i + kLongAhead);  // into the slot read one step ago, never the one just read
+        prefetch(i + kLongAhead, ahead_off);  // into the slot read one step ago, never the one just read
         uint32_t tw_text = 0, tw_time = 0;  // bit k: the cell of frame j0 + k takes the text step / the time step
         float c0 = diag_in;   // cost[i-1][j-1]
         float c2 = left_in;   // cost[i][j-1]
@@ -697,13 +707,11 @@ __global__ void __launch_bounds__(32 * WPP) dtw_align_long_kernel(const DtwLaunc
             c2 = cost;     // this column's new value is the next column's left
             up[k] = cost;
         }
-        const uint16_t tw = (uint16_t)(tw_text | (tw_time << kStripCols));
         diag_in = left_in;
         last_new = c2;
         if (act) {
-            if (n_cols > 0) trace[(size_t)i * L + g] = tw;
-            if (lane == 31 && warp < WPP - 1)
-                edge_out[i] = ((unsigned long long)(uint32_t)(i + 1) << 32) | __float_as_uint(last_new);
+            if (n_cols > 0) trace[trace_off] = (uint16_t)(tw_text | (tw_time << kStripCols));
+            if (publishes) edge_out[i] = ((unsigned long long)(uint32_t)(i + 1) << 32) | __float_as_uint(last_new);
         }
     }
     cp_async_wait<0>();
