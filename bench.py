@@ -18,6 +18,8 @@ Timed regions (CUDA events on the launching stream, barrier + synchronize on bot
 The same run also measures, at the same N, the other configurations BASELINE.json names (key `configs`):
     librispeech : configs[2] -- the FIXED list of 2620 LibriSpeech-shaped utterances (2-30 s) is drained once by the
                   N ranks (strong scaling: LPT shards by cost, length-bucketed batches); utt/s = 2620 / slowest rank
+    ami         : configs[3] -- AMI-shaped short segments (1-6 s, 5-25 subword tokens), Whisper-large-v3 dims (128 mels,
+                  32 x 20 heads), subword units, aggr=mean, the reference's default medfilt_width 7; weak scaling
     probe_sweep : configs[4] -- filter_attention over all 384 heads, then every head DTW'd on its own
                   (reference probe_oracle.py:82-90) through timing.probe_heads_batch; DTWs/s
 One JSON line on rank 0; see the task contract for the keys.
@@ -103,7 +105,7 @@ def parse():
     ap.add_argument("--profile-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed `value` region (for `ncu --profile-from-start off`)")
     ap.add_argument("--cpu-sample", type=int, default=10, help="utterances timed for cpu_baseline (0 = skip)")
-    ap.add_argument("--configs", default="librispeech,probe_sweep",
+    ap.add_argument("--configs", default="librispeech,ami,probe_sweep",
                     help="extra BASELINE.json configurations measured in the same run ('' = none)")
     ap.add_argument("--libri-utts", type=int, default=N_LIBRISPEECH, help="length of the fixed LibriSpeech-shaped list")
     ap.add_argument("--libri-batch", type=int, default=32, help="largest length-bucketed batch of the LibriSpeech drain")
@@ -499,6 +501,10 @@ def main():
         extra["librispeech"] = run_librispeech_drain(args, model, tk, dev, rank, world, peak, barrier, all_ranks)
     if "probe_sweep" in wanted:
         extra["probe_sweep"] = run_probe_sweep(args, model, tk, dev, rank, world, barrier, max_over_ranks)
+    if "ami" in wanted:
+        del model, resident
+        torch.cuda.empty_cache()
+        extra["ami"] = run_ami(args, dev, rank, world, peak, barrier, max_over_ranks)
 
     if rank == 0:
         cpu = None
@@ -623,6 +629,55 @@ def run_librispeech_drain(args, model, tk, dev, rank, world, peak, barrier, all_
                           "basis": "whole shard: sum of algorithmic bytes / sum of capture launch time"},
         "dtw_cells_per_s_rank0": my_cells / (dtw_ms / 1000.0) if dtw_ms > 0 else None,
         "stages_ms_rank0": {k: v[1] for k, v in sorted(km.items())},
+    }
+
+
+def run_ami(args, dev, rank, world, peak, barrier, max_over_ranks, batch=32, n_steps=3):
+    """BASELINE.json configs[3]: AMI-shaped short segments, Whisper-large-v3 dimensions (random init created on the device),
+    subword units, aggr=mean (upper half of the layers, timing.py:84-89), medfilt_width 7 (the reference CLI's default).
+    Every rank aligns its own batches (weak scaling); a step is one batch of 32 segments."""
+    from whisper_char_alignment_b200 import _cabi, synthetic, timing, whisper_model
+    from whisper_char_alignment_b200.tokenizer import get_tokenizer
+
+    dims = whisper_model.dims_for("large-v3")
+    model = whisper_model.random_init(dims, seed=0, qk_gain=4.0, device=dev)
+    tk = get_tokenizer(True, language="English", num_languages=model.num_languages)
+    L, H, d = dims.n_text_layer, dims.n_text_head, dims.n_text_state
+    pool = synthetic.ami_shaped(batch * 2, tk, n_mels=dims.n_mels, seed=4000 + rank)
+    groups = [pool[:batch], pool[batch:]]
+    res_in = [(torch.stack([u.mel for u in g]).to(dev), [u.tokens.to(dev) for u in g]) for g in groups]
+
+    def step(i):
+        g = groups[i % 2]
+        mels, toks = res_in[i % 2]
+        ws, _ = timing.get_attentions_batch(mels, toks, model, tk, [u.max_frames for u in g], 7, 1.0)
+        return timing.force_align_batch(ws, [u.text_tokens for u in g], tk, "subword", "mean")
+
+    step(0)
+    step(1)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with _cabi.KernelTimer() as kt:
+        e0.record()
+        for i in range(n_steps):
+            step(i)
+        e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    km = kt.summary()
+    cap_calls, cap_ms = km.get("wca_capture_attention", (0, 0.0))
+    by = float(sum(capture_bytes(groups[i % 2], L, H, d) for i in range(n_steps)))
+    gbs = by / (cap_ms / 1000.0) / 1e9 if cap_ms > 0 else 0.0
+    del model
+    torch.cuda.empty_cache()
+    return {
+        "workload": "AMI-shaped synthetic short segments (1-6 s, 5-25 subword tokens), Whisper-large-v3 dims (128 mels, 32 x 20 "
+                    "heads, random-init on the device), subword units, aggr=mean, medfilt_width=7",
+        "scaling": "weak", "n_gpus": world, "steps": n_steps, "utterances_per_step_per_gpu": batch,
+        "value": batch * n_steps * world / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms / n_steps,
+        "capture_rank0": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                          "ms_per_step": cap_ms / n_steps, "launches_per_step": cap_calls / n_steps},
+        "stages_ms_per_step_rank0": {k: v[1] / n_steps for k, v in sorted(km.items())},
     }
 
 

@@ -370,9 +370,22 @@ def load_model(name_or_path: str, device=None, *, seed: int = 0, qk_gain: float 
     return model if device is None else model.to(device)
 
 
-def random_init(dims: ModelDimensions, seed: int = 0, qk_gain: float = 1.0) -> Whisper:
+def random_init(dims: ModelDimensions, seed: int = 0, qk_gain: float = 1.0, device=None) -> Whisper:
     """Seeded synthetic weights.  `qk_gain` scales the cross-attention query/key projections
-    so that the maps are peaky enough for alignment paths to be data-driven."""
+    so that the maps are peaky enough for alignment paths to be data-driven.  With `device` the parameters are created
+    (and drawn) directly there -- seconds instead of a minute for large-v3 -- from that device's generator, i.e. NOT the
+    weights the same seed gives on the CPU (throughput runs only; parity runs share CPU-initialised weights with the oracle)."""
+    if device is not None and torch.device(device).type == "cuda":
+        with torch.device(device):
+            torch.cuda.manual_seed(seed)
+            model = Whisper(dims)
+            with torch.no_grad():
+                model.decoder.positional_embedding.normal_(0, 0.02)
+                for blk in model.decoder.blocks:
+                    blk.cross_attn.query.weight.mul_(qk_gain)
+                    blk.cross_attn.query.bias.mul_(qk_gain)
+                    blk.cross_attn.key.weight.mul_(qk_gain)
+        return model.eval()
     keep = torch.random.get_rng_state()
     torch.manual_seed(seed)
     model = Whisper(dims)
