@@ -138,20 +138,51 @@ struct Geo {
     float *col_ss;           // ... and sum_t p[t,f]^2, frame 0 ([4][F] floats); nullptr: not wanted
 };
 
+// Position of a role in the static tile schedule (tile = (utterance, layer * head, token block), tiles cid, cid + n_clusters,
+// ...): the three indices advance by carries instead of being divided out of the tile number for every tile -- all 16 warps of
+// a CTA walk the whole list, and the four divisions by run-time divisors were most of the ~120 instructions a tile cost each.
+struct TileCursor {
+    int tile, ub, lh, tb;
+    int d_ub, d_lh, d_tb;  // the stride, decomposed the same way
+    float rcp_heads, rcp_csize;
+    __device__ __forceinline__ void init(const KernelArgs &a, int first, int stride, uint32_t csize) {
+        tile = first;
+        tb = first % a.tok_blocks;
+        int r = first / a.tok_blocks;
+        lh = r % a.lh_count;
+        ub = r / a.lh_count;
+        d_tb = stride % a.tok_blocks;
+        r = stride / a.tok_blocks;
+        d_lh = r % a.lh_count;
+        d_ub = r / a.lh_count;
+        rcp_heads = 1.0f / (float)a.n_heads;
+        rcp_csize = 1.0f / (float)csize;
+    }
+    __device__ __forceinline__ void next(const KernelArgs &a, int stride) {
+        tile += stride;
+        tb += d_tb;
+        if (tb >= a.tok_blocks) { tb -= a.tok_blocks; ++lh; }
+        lh += d_lh;  // < 2 * lh_count: one correction is enough
+        if (lh >= a.lh_count) { lh -= a.lh_count; ++ub; }
+        ub += d_ub;
+    }
+};
+// x / d for 0 <= x < 2^15 and d <= 32 through the reciprocal: (x + 0.5) / d is at least 1 / 64 away from an integer and
+// the two roundings move it by less than x / d * 2^-22, so the floor is exact
+__device__ __forceinline__ int div_small(int x, float rcp) { return __float2int_rd(((float)x + 0.5f) * rcp); }
+
 template <int W>
-__device__ __forceinline__ Geo decode_tile(const KernelArgs &a, int tile, uint32_t crank, uint32_t csize) {
+__device__ __forceinline__ Geo decode_tile(const KernelArgs &a, const TileCursor &tc, uint32_t crank, uint32_t csize) {
     Geo g;
-    const int tb = tile % a.tok_blocks;
-    const int lh = (tile / a.tok_blocks) % a.lh_count;
-    const int ub = tile / (a.tok_blocks * a.lh_count);
-    const wca_utt_t u = a.utts[ub];
+    const int tb = tc.tb, lh = tc.lh;
+    const wca_utt_t u = a.utts[tc.ub];
     g.T = u.n_tokens;
     g.F = u.n_frames;
     const int t0 = tb * kRows;
     g.live = t0 < g.T;
     g.rows_valid = min(kRows, g.T - t0);
-    g.layer = lh / a.n_heads;
-    g.col0 = (lh % a.n_heads) * kHeadDim;
+    g.layer = div_small(lh, tc.rcp_heads);
+    g.col0 = (lh - g.layer * a.n_heads) * kHeadDim;
     g.qrow0 = (int)u.q_row0 + t0;
     g.krow0 = (int)u.k_row0;
     g.out = a.ws + u.ws_off + ((int64_t)lh * g.T + t0) * g.F;
@@ -164,7 +195,7 @@ __device__ __forceinline__ Geo decode_tile(const KernelArgs &a, int tile, uint32
         g.row_part = base + ((int64_t)lh * tbu + tb) * 4;
         g.col_ss = base + (int64_t)a.lh_count * tbu * 4 + ((int64_t)lh * tbu + tb) * 4 * g.F;
     }
-    const int slab = (((g.F + (int)csize - 1) / (int)csize) + 15) & ~15;
+    const int slab = (div_small(g.F + (int)csize - 1, tc.rcp_csize) + 15) & ~15;
     g.f0 = (int)crank * slab;
     g.f1 = min(g.F, g.f0 + slab);
     g.n_own = max(0, g.f1 - g.f0);
@@ -569,8 +600,9 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
         uint32_t n_tile = 0;
         const bool tr = a.trace && blockIdx.x == (a.dbg >> 8) && lane == 0;
         const uint32_t q_hi = smem_u32(smem + kOffQHi), k_hi = smem_u32(smem + kOffKHi);
-        for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
-            const Geo g = decode_tile<W>(a, tile, crank, csize);
+        TileCursor cur;
+        for (cur.init(a, cid, n_clusters, csize); cur.tile < a.n_tiles; cur.next(a, n_clusters)) {
+            const Geo g = decode_tile<W>(a, cur, crank, csize);
             if (!g.live || g.n_own == 0) continue;
             // K_hi is refilled as soon as the two MMA passes that read it have run (a third of the MMA time and the whole
             // drain earlier than the last pass), Q_hi once all of them have: the K load -- 60 % of the bytes -- is then
@@ -603,8 +635,9 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
             // While this tile is split, multiplied and filtered, pull the next tile's boxes into L2: the
             // operand buffers are single (shared memory is full), so the next load can only be issued once
             // this tile's MMAs are done, and its latency is then an L2 hit instead of an HBM round trip.
-            for (int nt = tile + n_clusters; nt < a.n_tiles; nt += n_clusters) {
-                const Geo h = decode_tile<W>(a, nt, crank, csize);
+            TileCursor ahead = cur;
+            for (ahead.next(a, n_clusters); ahead.tile < a.n_tiles; ahead.next(a, n_clusters)) {
+                const Geo h = decode_tile<W>(a, ahead, crank, csize);
                 if (!h.live || h.n_own == 0) continue;
                 if (lane == 0) {
                     const CUtensorMap *kmap = &maps.k[h.n_chunks - 1][h.layer];
@@ -631,8 +664,9 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
         const uint64_t da_lo = smem_desc_sw128(smem_u32(smem + kOffQLo), 16, 1024);
         const uint64_t db_hi = smem_desc_sw128(smem_u32(smem + kOffKHi), 16, 1024);
         const uint64_t db_lo = smem_desc_sw128(smem_u32(smem + kOffKLo), 16, 1024);
-        for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
-            const Geo g = decode_tile<W>(a, tile, crank, csize);
+        TileCursor cur;
+        for (cur.init(a, cid, n_clusters, csize); cur.tile < a.n_tiles; cur.next(a, n_clusters)) {
+            const Geo g = decode_tile<W>(a, cur, crank, csize);
             if (!g.live) continue;
             const uint32_t buf = it & 1u;
             ++it;
@@ -684,8 +718,9 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
         const int t = tid - 4 * 32;
         uint32_t n_tile = 0;
         const bool tr = a.trace && blockIdx.x == (a.dbg >> 8) && t == 0;
-        for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
-            const Geo g = decode_tile<W>(a, tile, crank, csize);
+        TileCursor cur;
+        for (cur.init(a, cid, n_clusters, csize); cur.tile < a.n_tiles; cur.next(a, n_clusters)) {
+            const Geo g = decode_tile<W>(a, cur, crank, csize);
             if (!g.live || g.n_own == 0) continue;
             mbar_wait(bar(kOpFree), (n_tile & 1u) ^ 1u);  // the previous tile's MMAs no longer read the lo twins (first lap passes)
             mbar_wait(bar(kKFull), n_tile & 1u);
@@ -727,13 +762,18 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
         const int grp = (warp - 8) >> 2, ewarp = warp & 3;
         uint32_t it = 0, acc_use = 0, n_x = 0;
         const bool tr = a.trace && blockIdx.x == (a.dbg >> 8) && ewarp == 0 && lane == 0;
-        for (int tile = cid; tile < a.n_tiles; tile += n_clusters) {
-            const Geo g = decode_tile<W>(a, tile, crank, csize);
-            if (!g.live) continue;
+        // the other warpgroup's tiles only have to be counted: a tile is live when its first token row exists
+        TileCursor cur;
+        for (cur.init(a, cid, n_clusters, csize); cur.tile < a.n_tiles; cur.next(a, n_clusters)) {
             const bool mine = (it & 1u) == (uint32_t)grp;
+            if (!mine) {
+                if (cur.tb * kRows < a.utts[cur.ub].n_tokens) ++it;
+                continue;
+            }
+            const Geo g = decode_tile<W>(a, cur, crank, csize);
+            if (!g.live) continue;
             const uint32_t seq = it;
             ++it;
-            if (!mine) continue;
             if (g.n_own > 0) {
                 mbar_wait(bar(kAccFull + grp), acc_use & 1u);
                 tc_fence_after();
