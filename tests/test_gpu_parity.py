@@ -524,6 +524,9 @@ def _torch_maps(q, k, heads, T, F, width_med, qk_scale):
     dict(id="c3_librispeech", heads=16, layers=2, tf=[(405, 1500), (448, 1111), (130, 449), (301, 897), (200, 1340), (70, 1345), (100, 672)], w=3),
     dict(id="c4_large_v3", heads=20, layers=3, tf=[(20, 200), (9, 57), (30, 300), (25, 225)], w=7),
     dict(id="c2_timit_w5", heads=16, layers=2, tf=[(45, 150), (64, 224), (65, 225), (128, 100), (129, 193)], w=5),
+    # utterances of at most w/2 frames are not filtered (timing.py:65 through upstream median_filter), the next ones are
+    dict(id="tiny_frames_w7", heads=8, layers=2, tf=[(5, 1), (7, 2), (9, 3), (40, 3), (70, 2), (130, 1), (6, 4), (12, 17)], w=7),
+    dict(id="tiny_frames_w3", heads=8, layers=1, tf=[(5, 1), (33, 1), (7, 2), (65, 2), (9, 16), (9, 17)], w=3),
 ], ids=lambda c: c["id"])
 def test_capture_at_baseline_shapes_vs_torch_fp32(cfg, dev):
     """BASELINE.json configs 2-4 at their real token / frame counts (layers cut to keep the test small):
