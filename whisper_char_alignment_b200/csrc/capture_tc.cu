@@ -248,7 +248,7 @@ struct Tail {
 };
 template <int W>
 __device__ __forceinline__ void median_block(const float (&ptail)[Tail<W>::kLen], const float (&cur)[16],
-                                             const float (&next)[16], float (&out)[16]) {
+                                             const float (&head)[4], float (&out)[16]) {
     constexpr int half = W / 2;
     if constexpr (W == 1) {
 #pragma unroll
@@ -261,7 +261,7 @@ __device__ __forceinline__ void median_block(const float (&ptail)[Tail<W>::kLen]
             const float lo = fminf(cur[2 * k], cur[2 * k + 1]);
             const float hi = fmaxf(cur[2 * k], cur[2 * k + 1]);
             const float left = k == 0 ? ptail[0] : cur[2 * k - 1];
-            const float right = k == 7 ? next[0] : cur[2 * k + 2];
+            const float right = k == 7 ? head[0] : cur[2 * k + 2];
             out[2 * k] = fmaxf(lo, fminf(hi, left));
             out[2 * k + 1] = fmaxf(lo, fminf(hi, right));
         }
@@ -272,25 +272,25 @@ __device__ __forceinline__ void median_block(const float (&ptail)[Tail<W>::kLen]
 #pragma unroll
             for (int j = 0; j < W; ++j) {
                 const int idx = pos - half + j;  // relative to cur[0]
-                win[j] = idx < 0 ? ptail[half + idx] : (idx < 16 ? cur[idx] : next[idx - 16]);
+                win[j] = idx < 0 ? ptail[half + idx] : (idx < 16 ? cur[idx] : head[idx - 16]);
             }
             out[pos] = median_regs<W>(win);
         }
     }
 }
 
-// One 16-column block of the fused filter / exponential sweep (epilogue_tile, sweep A+B).  `cur` is dead once
-// the filter has run, so the block after next is loaded straight into its registers: the caller alternates the
-// roles of the two buffers instead of moving 32 registers per block.
+// One 16-column block of the fused filter / exponential sweep (epilogue_tile, sweep A+B).  `cur` and `head` (the first
+// columns of the next block: all the window needs of it) are dead once the filter has run, so the next block and the
+// head of the one after it are loaded straight into their registers and land behind the exponentials.
 struct RowStats {
     float m2, row_sum, row_ss;  // lazy reference (log2 domain), sum of e = 2^(y - m2), sum of e^2
 };
 template <int W>
-__device__ __forceinline__ void filter_exp_block(uint32_t trow, int b, int b_lo, int n_blocks, int tail, bool filter,
+__device__ __forceinline__ void filter_exp_block(uint32_t trow, int b, int b_lo, int b_hi, int n_blocks, int tail, bool filter,
                                                  float scale2, float (&ptail)[Tail<W>::kLen], float (&cur)[16],
-                                                 float (&next)[16], RowStats &st, bool want_ss) {
+                                                 float (&head)[4], RowStats &st, bool want_ss) {
     float med[16];
-    median_block<W>(ptail, cur, next, med);
+    median_block<W>(ptail, cur, head, med);
     if (W > 1 && !filter) {  // rows of at most W/2 frames are not filtered (as upstream): rare, kept off the hot path
 #pragma unroll
         for (int i = 0; i < 16; ++i) med[i] = cur[i];
@@ -299,7 +299,10 @@ __device__ __forceinline__ void filter_exp_block(uint32_t trow, int b, int b_lo,
 #pragma unroll
         for (int j = 0; j < W / 2; ++j) ptail[j] = cur[16 - W / 2 + j];
     }
-    if (b + 2 <= n_blocks) tmem_ld16_issue(trow + (uint32_t)(16 * (b + 2)), cur);  // stays inside the accumulator
+    if (b + 1 < b_hi) {
+        tmem_ld16_issue(trow + (uint32_t)(16 * (b + 1)), cur);
+        if (W > 1) tmem_ld4_issue(trow + (uint32_t)(16 * (b + 2)), head);  // b + 2 <= n_blocks: stays inside the accumulator
+    }
     const int n_ok = b + 1 < n_blocks ? 16 : tail;
     if (n_ok < 16) {  // last block: columns past the row end must not win the maximum
 #pragma unroll
@@ -328,13 +331,13 @@ __device__ __forceinline__ void filter_exp_block(uint32_t trow, int b, int b_lo,
         st.row_sum *= f;
         st.row_ss *= f * f;
 #pragma unroll 1
-        for (int bb = b_lo; bb < b; ++bb) {
-            float t[16];
-            tmem_ld16_issue(trow + (uint32_t)(16 * bb), t);
-            tmem_ld_wait(t);
+        for (int cc = 16 * b_lo; cc < 16 * b; cc += 4) {
+            float t[4];
+            tmem_ld4_issue(trow + (uint32_t)cc, t);
+            tmem_ld_wait4(t);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) t[i] *= f;
-            tmem_st16(trow + (uint32_t)(16 * bb), t);
+            for (int i = 0; i < 4; ++i) t[i] *= f;
+            tmem_st4(trow + (uint32_t)cc, t);
         }
     }
     const float neg_m2 = -st.m2;
@@ -358,7 +361,8 @@ __device__ __forceinline__ void filter_exp_block(uint32_t trow, int b, int b_lo,
         st.row_ss += q0 + q1;
     }
     tmem_st16(trow + (uint32_t)(16 * b), med);
-    tmem_ld_wait(cur);  // the block after next has landed (also orders the loads of the rescale path)
+    tmem_ld_wait(cur);  // the next block (and the head of the one after it) has landed; also orders the loads of the rescale path
+    tmem_ld_wait4(head);
 }
 
 // The three sweeps of one tile by one epilogue warpgroup (thread <-> token row).
@@ -406,24 +410,21 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
         const bool want_ss = g.row_part != nullptr && !(a.dbg & 0x400u);  // (0x400: experiment switch)
         RowStats st{-INFINITY, 0.f, 0.f};
         if (sweep) {
-            float ptail[Tail<W>::kLen], bufa[16], bufb[16];
+            float ptail[Tail<W>::kLen], cur[16], head[4];
             {
-                float prev[16];
-                tmem_ld16_issue(trow + (uint32_t)(16 * b_lo) - 16u, prev);
-                tmem_ld16_issue(trow + (uint32_t)(16 * b_lo), bufa);
-                tmem_ld16_issue(trow + (uint32_t)(16 * (b_lo + 1)), bufb);
-                tmem_ld_wait(prev);
-                tmem_ld_wait(bufa);
-                tmem_ld_wait(bufb);
+                float prev[4];
+                tmem_ld4_issue(trow + (uint32_t)(16 * b_lo) - 4u, prev);
+                tmem_ld16_issue(trow + (uint32_t)(16 * b_lo), cur);
+                tmem_ld4_issue(trow + (uint32_t)(16 * (b_lo + 1)), head);
+                tmem_ld_wait4(prev);
+                tmem_ld_wait(cur);
+                tmem_ld_wait4(head);
 #pragma unroll
-                for (int j = 0; j < Tail<W>::kLen; ++j) ptail[j] = prev[16 - Tail<W>::kLen + j];
+                for (int j = 0; j < Tail<W>::kLen; ++j) ptail[j] = prev[4 - Tail<W>::kLen + j];
             }
 #pragma unroll 1
-            for (int b = b_lo; b < b_hi; b += 2) {
-                filter_exp_block<W>(trow, b, b_lo, n_blocks, tail, g.half > 0, scale2, ptail, bufa, bufb, st, want_ss);
-                if (b + 1 < b_hi)
-                    filter_exp_block<W>(trow, b + 1, b_lo, n_blocks, tail, g.half > 0, scale2, ptail, bufb, bufa, st, want_ss);
-            }
+            for (int b = b_lo; b < b_hi; ++b)
+                filter_exp_block<W>(trow, b, b_lo, b_hi, n_blocks, tail, g.half > 0, scale2, ptail, cur, head, st, want_ss);
             tmem_wait_st();
         }
         const float m2 = st.m2, row_sum = st.row_sum, row_ss = st.row_ss;

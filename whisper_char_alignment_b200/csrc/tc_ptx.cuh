@@ -189,6 +189,21 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
         "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
         : "memory");
 }
+// four-column variants (edges of the median window, rare in-place rescale)
+__device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, float (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait4(float (&v)[4]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]) : : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3])
+                 : "memory");
+}
 __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
     float r;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;"
