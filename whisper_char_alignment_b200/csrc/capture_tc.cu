@@ -330,6 +330,7 @@ __device__ __forceinline__ void filter_exp_block(uint32_t trow, int b, int b_lo,
         if (need) st.m2 = bmax;
         st.row_sum *= f;
         st.row_ss *= f * f;
+        tmem_wait_st();  // the blocks stored so far are read back
 #pragma unroll 1
         for (int cc = 16 * b_lo; cc < 16 * b; cc += 4) {
             float t[4];
@@ -393,15 +394,17 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
     bool report_rows = false;
     float row_term = 0.f;
     if (!a.raw_logits) {
-        if (rows_live && g.half > 0) {
-            {
-                // materialise the reflect padding in TMEM: frame -i <- frame i, frame F-1+i <- frame F-1-i
-                if (g.f0 == 0)
-                    for (int i = 1; i <= g.half; ++i) tmem_st1(trow - (uint32_t)i, tmem_ld1(trow + (uint32_t)i));
-                for (int f = max(g.F, g.f1); f < g.f1 + g.half; ++f)
-                    tmem_st1(trow + (uint32_t)(f - g.f0), tmem_ld1(trow + (uint32_t)(2 * (g.F - 1) - f - g.f0)));
-                tmem_wait_st();
-            }
+        if (sweep && g.half > 0 && min(g.f1, g.f0 + 16 * b_hi) + g.half > g.F) {  // the windows of this part reach past the last frame
+            // materialise the right reflect padding in TMEM, frame F-1+i <- frame F-1-i (i = 1..3 whatever the width: what a
+            // narrower window does not read is never used): one 4-column load and one 4-column store instead of a round
+            // trip per frame.  (The left padding never reaches tensor memory: see ptail below.)
+            float t[4];
+            const uint32_t c_end = trow + (uint32_t)(g.F - g.f0);
+            tmem_ld4_issue(c_end - 4u, t);
+            tmem_ld_wait4(t);
+            const float r[4] = {t[2], t[1], t[0], t[0]};
+            tmem_st4(c_end, r);
+            tmem_wait_st();
         }
         // Sweep A+B fused: median filter, * qk_scale, and e = 2^(y - m) against a LAZY per-thread reference m
         // (the maximum of the thread's first block; it only moves when a later block exceeds it by 2^32, and the
@@ -423,11 +426,14 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
                 tmem_ld_wait4(head);
 #pragma unroll
                 for (int j = 0; j < Tail<W>::kLen; ++j) ptail[j] = prev[4 - Tail<W>::kLen + j];
+                if (W > 1 && g.f0 == 0 && b_lo == 0) {  // left reflect padding: frame -i <- frame i, straight from the first block
+#pragma unroll
+                    for (int j = 0; j < Tail<W>::kLen; ++j) ptail[j] = cur[Tail<W>::kLen - j];
+                }
             }
 #pragma unroll 1
             for (int b = b_lo; b < b_hi; ++b)
                 filter_exp_block<W>(trow, b, b_lo, b_hi, n_blocks, tail, g.half > 0, scale2, ptail, cur, head, st, want_ss);
-            tmem_wait_st();
         }
         const float m2 = st.m2, row_sum = st.row_sum, row_ss = st.row_ss;
         stamp(tr, seq, kEvEpiA);
@@ -439,7 +445,7 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
         float gmax = m2, gsum = row_sum, gss = row_ss;
         if (g.dup) {
             strip[ewarp * 32 + lane] = make_float4(m2, row_sum, row_ss, 0.f);
-            named_bar_sync(1 + grp, kEpiThreads);
+            named_bar_sync(3 + grp * 2 + (ewarp & 1), 64);  // only the two warps that hold the same rows meet
             const float4 o = strip[(ewarp ^ 2) * 32 + lane];
             gmax = fmaxf(m2, o.x);
             const float fa = m2 > -INFINITY ? ex2_approx(m2 - gmax) : 0.f, fb = o.x > -INFINITY ? ex2_approx(o.x - gmax) : 0.f;
@@ -478,7 +484,7 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
         // (the shuffle tree and the store wait until the store sweep is through: they are not on the way to the accumulator's release)
         report_rows = g.row_part != nullptr && rows_live && (csize == 1 || cluster_ctarank() == 0) && (!g.dup || ewarp < 2);
         if (report_rows) row_term = row_ok ? sqrtf(gss) / gsum : 0.f;
-        inv_sum = (m2 > -INFINITY ? ex2_approx(m2 - gmax) : 0.f) / gsum;  // this thread's e values are relative to its own m
+        inv_sum = __fdividef(m2 > -INFINITY ? ex2_approx(m2 - gmax) : 0.f, gsum);  // this thread's e values are relative to its own m
         // lanes past the last token row hold finite values nobody stores; as exact zeros in the transposition tile they also
         // drop out of the column sums of the head scores without a per-element predicate
         if (g.col_ss != nullptr && !row_ok) inv_sum = 0.f;
@@ -509,6 +515,7 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
 #pragma unroll
         for (int j = 0; j < 4; ++j) tsrc[j] = tile + rsel * kTilePitch + 4 * ((c >> 2) ^ j) + (c & 3);
         float v[16];
+        tmem_wait_st();  // the filter sweep's stores (they drained behind the statistics exchange)
         tmem_ld16_issue(trow + (uint32_t)(16 * b_lo), v);
         tmem_ld_wait(v);
         for (int b = b_lo; b < b_hi; ++b) {
