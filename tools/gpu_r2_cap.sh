@@ -4,7 +4,7 @@
 for lib in "" tools/libwca_*.so; do
   [ -n "$lib" ] && [ ! -f "$lib" ] && continue
   echo "== lib: ${lib:-current}"
-  for shape in "timit 32" "libri 8"; do
+  for shape in "timit 32" "libri 8" "ami 32"; do
     WCA_LIB=$lib WCA_PARTIALS=1 python tools/ncu_capture.py $shape
   done
 done

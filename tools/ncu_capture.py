@@ -1,4 +1,4 @@
-"""One capture launch at a BASELINE.json shape, for ncu.  usage: ncu_capture.py [timit|libri] [B] [simt]"""
+"""One capture launch at a BASELINE.json shape, for ncu.  usage: ncu_capture.py [timit|libri|ami] [B] [simt]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -12,9 +12,13 @@ simt = len(sys.argv) > 3 and sys.argv[3] == "simt"
 reps = int(os.environ.get("WCA_REPS", "20"))
 dev = torch.device("cuda:0")
 L, H, D, n_ctx = 24, 16, 64, 1500
+width = 3
 rng = np.random.default_rng(0)
 if shape == "timit":
     Ts = rng.integers(35, 56, B); Fs = rng.integers(100, 200, B)
+elif shape == "ami":  # BASELINE configs[3]: large-v3 dims, short segments, subword tokens, medfilt 7
+    L, H, width = 32, 20, 7
+    Ts = rng.integers(10, 31, B); Fs = rng.integers(50, 300, B)
 else:
     Fs = rng.integers(100, 1500, B); Ts = np.minimum(448, (Fs * 0.27).astype(int) + 5)
 t_max = int(Ts.max())
@@ -45,7 +49,7 @@ if os.environ.get("WCA_PARTIALS", "0") == "1" and not simt:  # head-score partia
 def capture():
     for sub, d in launches:
         _cabi.capture_attention(q, k, H, H * D, H * D, d, len(sub), int(sub["n_tokens"].max()), int(sub["n_frames"].max()),
-                                3, 1.0, ws, flags, partials)
+                                width, 1.0, ws, flags, partials)
 
 bytes_alg = 4 * off + sum(4 * L * (int(t) + int(f)) * H * D for t, f in zip(Ts, Fs))
 for _ in range(10):

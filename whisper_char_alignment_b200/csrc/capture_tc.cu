@@ -108,7 +108,7 @@ __device__ __forceinline__ void stamp(bool on, uint32_t tile_seq, int ev) {
 // one TMA instruction costs ~150 cycles of the producer lane whatever it moves, so a tile is fetched
 // with the tallest box that fits (K slab: one box per column half).
 struct TensorMaps {
-    CUtensorMap q[2][WCA_MAX_LAYERS];  // [box rows / 64 - 1]
+    CUtensorMap q[3][WCA_MAX_LAYERS];  // boxes of 64, 128 and 32 token rows
     CUtensorMap k[4][WCA_MAX_LAYERS];
 };
 
@@ -130,7 +130,9 @@ struct Geo {
     int half;                // filter half-width actually applied (0: identity)
     int m0, mcol0, n_mma;    // first frame / accumulator column / frame count the MMA computes
     int n_chunks;
-    bool dup;                // <= 64 token rows and a single-CTA cluster: rows are mirrored into A rows 64..127
+    int copies;              // single-CTA cluster: <= 64 token rows are mirrored into A rows 64..127 (2), <= 32 rows into all four
+                             // lane quarters (4): the epilogue warps that hold the same rows split the frames
+    bool dup;                // copies > 1
     int layer, col0;         // decoder layer and first float column of the head
     int qrow0, krow0;        // first Q row of the tile / first K row of the utterance
     float *out;              // row 0 of this tile, frame 0
@@ -205,7 +207,8 @@ __device__ __forceinline__ Geo decode_tile(const KernelArgs &a, const TileCursor
     g.mcol0 = g.f0 > 0 ? 0 : kOwnCol0;  // frame f always sits at accumulator column f - f0 + 16
     g.n_mma = g.n_own > 0 ? min(g.f1 + kHalo, g.F) - g.m0 : 0;
     g.n_chunks = (g.n_mma + kChunk - 1) / kChunk;
-    g.dup = csize == 1 && g.rows_valid <= kStageRows;
+    g.copies = csize == 1 ? (g.rows_valid <= 32 ? 4 : (g.rows_valid <= kStageRows ? 2 : 1)) : 1;
+    g.dup = g.copies > 1;
     return g;
 }
 
@@ -237,6 +240,20 @@ __device__ __forceinline__ void split_lo_dup(const unsigned char *hi, unsigned c
         const float4 l = make_float4(tf32_lo(v[it].x), tf32_lo(v[it].y), tf32_lo(v[it].z), tf32_lo(v[it].w));
         dst[it * kSplitThreads + t] = l;
         dst[kBoxBytes / 16 + it * kSplitThreads + t] = l;
+    }
+}
+
+// Four copies of a 32-row box (Geo::copies == 4): 4 KB read, its lo twin written four times.
+__device__ __forceinline__ void split_lo_quad(const unsigned char *hi, unsigned char *lo, int t) {
+    constexpr int kIters = kBoxBytes / 2 / 16 / kSplitThreads;  // 2
+    const float4 *src = reinterpret_cast<const float4 *>(hi);
+    float4 *dst = reinterpret_cast<float4 *>(lo);
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+        const float4 v = src[it * kSplitThreads + t];
+        const float4 l = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dst[c * (kBoxBytes / 2 / 16) + it * kSplitThreads + t] = l;
     }
 }
 
@@ -376,13 +393,15 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
     bool released = false;
     // Mirrored tiles (Geo::dup): lane quarters 2 and 3 hold a copy of token rows 0..63, so warps
     // 2/3 (other two schedulers) take the second half of the columns of the rows of warps 0/1.
-    const int lw = g.dup ? (ewarp & 1) : ewarp;  // logical 32-row group
+    const int copy = g.copies == 4 ? ewarp : (g.copies == 2 ? ewarp >> 1 : 0);     // which copy of the rows this warp holds
+    const int lw = g.copies == 4 ? 0 : (g.copies == 2 ? (ewarp & 1) : ewarp);      // logical 32-row group
     const int row = lw * 32 + lane;
     const bool row_ok = row < g.rows_valid;
     const int n_blocks = (g.n_own + 15) >> 4;
-    const int split = g.dup ? (n_blocks + 1) >> 1 : n_blocks;
-    const int b_lo = (g.dup && ewarp >= 2) ? split : 0;
-    const int b_hi = (g.dup && ewarp >= 2) ? n_blocks : split;
+    // the copies split the blocks: copy p takes [ceil(n p / copies), ceil(n (p + 1) / copies))
+    const int cshift = g.copies >> 1;  // log2(copies) for 1, 2, 4
+    const int b_lo = (n_blocks * copy + g.copies - 1) >> cshift;
+    const int b_hi = (n_blocks * (copy + 1) + g.copies - 1) >> cshift;
     const bool rows_live = (lw * 32 < g.rows_valid) && g.n_own > 0;  // warp-uniform
     const bool sweep = rows_live && b_lo < b_hi;
     const uint32_t trow = acc + ((uint32_t)(ewarp * 32) << 16) + kOwnCol0;  // own frame 0 of this lane quarter
@@ -443,7 +462,7 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
         // statistics buffers alternate with the tile parity so that nobody overwrites a triple a slower peer still reads
         float4 *strip = sstat + x_parity * kRows;
         float gmax = m2, gsum = row_sum, gss = row_ss;
-        if (g.dup) {
+        if (g.copies == 2) {
             strip[ewarp * 32 + lane] = make_float4(m2, row_sum, row_ss, 0.f);
             named_bar_sync(3 + grp * 2 + (ewarp & 1), 64);  // only the two warps that hold the same rows meet
             const float4 o = strip[(ewarp ^ 2) * 32 + lane];
@@ -451,6 +470,21 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
             const float fa = m2 > -INFINITY ? ex2_approx(m2 - gmax) : 0.f, fb = o.x > -INFINITY ? ex2_approx(o.x - gmax) : 0.f;
             gsum = row_sum * fa + o.y * fb;
             gss = row_ss * (fa * fa) + o.z * (fb * fb);
+        } else if (g.copies == 4) {
+            strip[ewarp * 32 + lane] = make_float4(m2, row_sum, row_ss, 0.f);
+            named_bar_sync(1 + grp, kEpiThreads);  // all four warps hold the same 32 rows
+            float4 pr[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pr[j] = strip[j * 32 + lane];
+            gmax = fmaxf(fmaxf(pr[0].x, pr[1].x), fmaxf(pr[2].x, pr[3].x));
+            gsum = gss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)  // fixed order: every copy computes the same sums
+                if (pr[j].x > -INFINITY) {
+                    const float f = ex2_approx(pr[j].x - gmax);
+                    gsum += pr[j].y * f;
+                    gss += pr[j].z * (f * f);
+                }
         }
         if (csize > 1) {
             // every CTA of the cluster takes part, even with no own frames
@@ -482,7 +516,7 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
         // head scores, row term of this warp's 32 token rows (timing.py:24): one thread per row reports -- rank 0 of a
         // cluster, the first copy of a mirrored row -- and a fixed shuffle tree adds them (deterministic)
         // (the shuffle tree and the store wait until the store sweep is through: they are not on the way to the accumulator's release)
-        report_rows = g.row_part != nullptr && rows_live && (csize == 1 || cluster_ctarank() == 0) && (!g.dup || ewarp < 2);
+        report_rows = g.row_part != nullptr && rows_live && (csize == 1 || cluster_ctarank() == 0) && copy == 0;
         if (report_rows) row_term = row_ok ? sqrtf(gss) / gsum : 0.f;
         inv_sum = __fdividef(m2 > -INFINITY ? ex2_approx(m2 - gmax) : 0.f, gsum);  // this thread's e values are relative to its own m
         // lanes past the last token row hold finite values nobody stores; as exact zeros in the transposition tile they also
@@ -631,13 +665,12 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
                 // Q rows 64..127: the next 64 token rows, or (Geo::dup) a second copy of rows 0..63; with <= 64
                 // rows and no mirroring the upper half is left as it is (nobody reads those lanes)
                 mbar_expect_tx(bar(kQFull), upper ? kQBytes : kQBytes / 2);
-                const CUtensorMap *qmap = &maps.q[(upper && !g.dup) ? 1 : 0][g.layer];
-                for (int half = 0; half < 2; ++half) {
-                    tma_load_box(q_hi + half * kQHalfBytes, qmap, g.col0 + half * kBoxCols, g.qrow0, bar(kQFull));
-                    if (g.dup)
-                        tma_load_box(q_hi + half * kQHalfBytes + kBoxBytes, qmap, g.col0 + half * kBoxCols, g.qrow0,
+                const CUtensorMap *qmap = &maps.q[g.copies == 4 ? 2 : ((upper && !g.dup) ? 1 : 0)][g.layer];
+                const int copy_bytes = kQHalfBytes >> (g.copies >> 1);  // one box per copy and column half
+                for (int half = 0; half < 2; ++half)
+                    for (int c = 0; c < g.copies; ++c)
+                        tma_load_box(q_hi + half * kQHalfBytes + c * copy_bytes, qmap, g.col0 + half * kBoxCols, g.qrow0,
                                      bar(kQFull));
-                }
             }
             __syncwarp();
             stamp(tr, n_tile, kEvProdQ);
@@ -651,7 +684,7 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
                 if (!h.live || h.n_own == 0) continue;
                 if (lane == 0) {
                     const CUtensorMap *kmap = &maps.k[h.n_chunks - 1][h.layer];
-                    const CUtensorMap *qmap = &maps.q[(!h.dup && h.rows_valid > kStageRows) ? 1 : 0][h.layer];
+                    const CUtensorMap *qmap = &maps.q[h.copies == 4 ? 2 : ((!h.dup && h.rows_valid > kStageRows) ? 1 : 0)][h.layer];
                     for (int half = 0; half < 2; ++half) {
                         tma_prefetch_box(kmap, h.col0 + half * kBoxCols, h.krow0 + h.m0);
                         tma_prefetch_box(qmap, h.col0 + half * kBoxCols, h.qrow0);
@@ -735,17 +768,6 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
             mbar_wait(bar(kOpFree), (n_tile & 1u) ^ 1u);  // the previous tile's MMAs no longer read the lo twins (first lap passes)
             mbar_wait(bar(kKFull), n_tile & 1u);
             stamp(tr, n_tile, kEvSplFull);
-            if (a.dbg & 0x100u) {  // experiment: Q twin first
-                mbar_wait(bar(kQFull), n_tile & 1u);
-                if (g.dup) {
-                    for (int half = 0; half < 2; ++half)
-                        split_lo_dup(smem + kOffQHi + half * kQHalfBytes, smem + kOffQLo + half * kQHalfBytes, t);
-                } else {
-                    split_lo<kQBytes>(smem + kOffQHi, smem + kOffQLo, t);
-                }
-                fence_proxy_async_smem();
-                mbar_arrive(bar(kQLoReady));
-            }
             for (int half = 0; half < 2; ++half)
                 for (int c = 0; c < g.n_chunks; ++c)
                     split_lo<kBoxBytes>(smem + kOffKHi + half * kKHalfBytes + c * kBoxBytes,
@@ -753,17 +775,18 @@ capture_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
             fence_proxy_async_smem();  // generic-proxy stores must be visible to the tensor core's async proxy
             mbar_arrive(bar(kKLoReady));
             stamp(tr, n_tile, kEvSplK0Done);
-            if (!(a.dbg & 0x100u)) {
-                mbar_wait(bar(kQFull), n_tile & 1u);
-                if (g.dup) {
-                    for (int half = 0; half < 2; ++half)
-                        split_lo_dup(smem + kOffQHi + half * kQHalfBytes, smem + kOffQLo + half * kQHalfBytes, t);
-                } else {
-                    split_lo<kQBytes>(smem + kOffQHi, smem + kOffQLo, t);
-                }
-                fence_proxy_async_smem();
-                mbar_arrive(bar(kQLoReady));
+            mbar_wait(bar(kQFull), n_tile & 1u);
+            if (g.copies == 4) {
+                for (int half = 0; half < 2; ++half)
+                    split_lo_quad(smem + kOffQHi + half * kQHalfBytes, smem + kOffQLo + half * kQHalfBytes, t);
+            } else if (g.copies == 2) {
+                for (int half = 0; half < 2; ++half)
+                    split_lo_dup(smem + kOffQHi + half * kQHalfBytes, smem + kOffQLo + half * kQHalfBytes, t);
+            } else {
+                split_lo<kQBytes>(smem + kOffQHi, smem + kOffQLo, t);
             }
+            fence_proxy_async_smem();
+            mbar_arrive(bar(kQLoReady));
             stamp(tr, n_tile, kEvSplQDone);
             ++n_tile;
         }
@@ -902,9 +925,9 @@ int launch_capture_tc(const float *const *h_q_layers, const float *const *h_k_la
     if (!hit) {
         memset(&maps, 0, sizeof(maps));
         for (int l = 0; l < n_layers; ++l) {
-            for (int v = 0; v < 2; ++v) {
+            for (int v = 0; v < 3; ++v) {
                 const int rc = encode_map(encode, &maps.q[v][l], h_q_layers[l], q_rows, (int64_t)n_heads * kHeadDim, ld_q,
-                                          (v + 1) * tc::kStageRows);
+                                          v == 2 ? tc::kStageRows / 2 : (v + 1) * tc::kStageRows);
                 if (rc) return rc;
             }
             for (int v = 0; v < 4; ++v) {
