@@ -72,8 +72,9 @@ constexpr int kOffQLo = kOffQHi + kQBytes;
 constexpr int kOffKHi = kOffQLo + kQBytes;
 constexpr int kOffKLo = kOffKHi + kKBytes;
 constexpr int kOffTile = kOffKLo + kKBytes;                     // 8 epilogue warps x 32 x 17 floats
-constexpr int kOffStat = kOffTile + 8 * 32 * kTilePitch * 4;    // [group][tile parity][128] x {m, sum, sum of squares, -}
-constexpr int kOffBar = kOffStat + 2 * 2 * kRows * 16;
+constexpr int kStatSlots = 2 * kRows;  // per group and tile parity: [128] published rows + [128] triples of the mirrored copies
+constexpr int kOffStat = kOffTile + 8 * 32 * kTilePitch * 4;    // [group][tile parity][256] x {m, sum, sum of squares, -}
+constexpr int kOffBar = kOffStat + 2 * 2 * kStatSlots * 16;
 enum Bar {
     kKFull = 0,                  // TMA -> splitters (transaction bytes): K slab landed
     kQFull = kKFull + 1,         // ... Q tile landed
@@ -130,7 +131,7 @@ struct Geo {
     int half;                // filter half-width actually applied (0: identity)
     int m0, mcol0, n_mma;    // first frame / accumulator column / frame count the MMA computes
     int n_chunks;
-    int copies;              // single-CTA cluster: <= 64 token rows are mirrored into A rows 64..127 (2), <= 32 rows into all four
+    int copies;              // <= 64 token rows are mirrored into A rows 64..127 (2), <= 32 rows into all four
                              // lane quarters (4): the epilogue warps that hold the same rows split the frames
     bool dup;                // copies > 1
     int layer, col0;         // decoder layer and first float column of the head
@@ -207,7 +208,7 @@ __device__ __forceinline__ Geo decode_tile(const KernelArgs &a, const TileCursor
     g.mcol0 = g.f0 > 0 ? 0 : kOwnCol0;  // frame f always sits at accumulator column f - f0 + 16
     g.n_mma = g.n_own > 0 ? min(g.f1 + kHalo, g.F) - g.m0 : 0;
     g.n_chunks = (g.n_mma + kChunk - 1) / kChunk;
-    g.copies = csize == 1 ? (g.rows_valid <= 32 ? 4 : (g.rows_valid <= kStageRows ? 2 : 1)) : 1;
+    g.copies = g.rows_valid <= 32 ? 4 : (g.rows_valid <= kStageRows ? 2 : 1);
     g.dup = g.copies > 1;
     return g;
 }
@@ -406,7 +407,7 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
     const bool sweep = rows_live && b_lo < b_hi;
     const uint32_t trow = acc + ((uint32_t)(ewarp * 32) << 16) + kOwnCol0;  // own frame 0 of this lane quarter
     const int tail = g.n_own - 16 * (n_blocks - 1);  // valid columns of the last block (1..16)
-    float4 *sstat = reinterpret_cast<float4 *>(smem + kOffStat) + grp * 2 * kRows;  // [tile parity][128] x {m, sum, ss, -}
+    float4 *sstat = reinterpret_cast<float4 *>(smem + kOffStat) + grp * 2 * kStatSlots;  // [tile parity][256] x {m, sum, ss, -}
     const uint32_t bar_xmax = smem_u32(smem + kOffBar) + 8u * (kXMax + grp);
 
     float inv_sum = a.s;  // raw-logit mode: only the 2^-3 of the operand scaling is applied
@@ -460,9 +461,9 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
         stamp(tr, seq, kEvEpiB);
         // (m, sum, sum of squares) of the other column half (mirrored tiles) and of the other cluster ranks; the
         // statistics buffers alternate with the tile parity so that nobody overwrites a triple a slower peer still reads
-        float4 *strip = sstat + x_parity * kRows;
+        float4 *strip = sstat + x_parity * kStatSlots;
         float gmax = m2, gsum = row_sum, gss = row_ss;
-        if (g.copies == 2) {
+        if (csize == 1 && g.copies == 2) {
             strip[ewarp * 32 + lane] = make_float4(m2, row_sum, row_ss, 0.f);
             named_bar_sync(3 + grp * 2 + (ewarp & 1), 64);  // only the two warps that hold the same rows meet
             const float4 o = strip[(ewarp ^ 2) * 32 + lane];
@@ -470,7 +471,7 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
             const float fa = m2 > -INFINITY ? ex2_approx(m2 - gmax) : 0.f, fb = o.x > -INFINITY ? ex2_approx(o.x - gmax) : 0.f;
             gsum = row_sum * fa + o.y * fb;
             gss = row_ss * (fa * fa) + o.z * (fb * fb);
-        } else if (g.copies == 4) {
+        } else if (csize == 1 && g.copies == 4) {
             strip[ewarp * 32 + lane] = make_float4(m2, row_sum, row_ss, 0.f);
             named_bar_sync(1 + grp, kEpiThreads);  // all four warps hold the same 32 rows
             float4 pr[4];
@@ -488,11 +489,35 @@ __device__ __forceinline__ bool epilogue_tile(const Geo &g, const KernelArgs &a,
         }
         if (csize > 1) {
             // every CTA of the cluster takes part, even with no own frames
-            strip[row] = row_ok ? make_float4(m2, row_sum, row_ss, 0.f) : make_float4(-INFINITY, 0.f, 0.f, 0.f);
+            const float4 mine = row_ok ? make_float4(m2, row_sum, row_ss, 0.f) : make_float4(-INFINITY, 0.f, 0.f, 0.f);
+            if (g.copies == 1) {
+                strip[row] = mine;
+            } else {
+                // mirrored rows: the copies' triples meet in the second half of the strip, the first copy adds them up
+                // (fixed order) and publishes the CTA's triple of the row for the other ranks
+                float4 *loc = strip + kRows;
+                loc[ewarp * 32 + lane] = mine;
+                named_bar_sync(7 + grp, kEpiThreads);
+                if (copy == 0) {
+                    const int stride = g.copies == 4 ? 32 : 64;  // warp of copy c with the same rows: ewarp + c * (4 / copies)
+                    float cm = -INFINITY;
+                    for (int c = 0; c < g.copies; ++c) cm = fmaxf(cm, loc[ewarp * 32 + c * stride + lane].x);
+                    float cs = 0.f, cq = 0.f;
+                    for (int c = 0; c < g.copies; ++c) {
+                        const float4 o = loc[ewarp * 32 + c * stride + lane];
+                        if (o.x > -INFINITY) {
+                            const float f = ex2_approx(o.x - cm);
+                            cs += o.y * f;
+                            cq += o.z * (f * f);
+                        }
+                    }
+                    strip[row] = make_float4(cm, cs, cq, 0.f);
+                }
+            }
             named_bar_sync(1 + grp, kEpiThreads);
             // lane r of the first warp signals rank r: ONE instruction with csize active lanes.  A loop of release-arrives
             // in one thread paid the cluster-scope release (~1.2 k cycles) once per rank, 9-10 k cycles per head.
-            if ((uint32_t)row < csize) mbar_arrive_remote(bar_xmax, (uint32_t)row);
+            if (ewarp == 0 && (uint32_t)lane < csize) mbar_arrive_remote(bar_xmax, (uint32_t)lane);
             mbar_wait_cluster(bar_xmax, x_parity);
             // all ranks' triples in flight at once: a dependent chain of remote loads (maximum first, then a conditional
             // load of each sum) cost ~16 distributed-shared-memory round trips per head, 10.8 k of a 22.7 k-cycle epilogue
