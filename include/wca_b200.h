@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define WCA_ABI_VERSION 4
+#define WCA_ABI_VERSION 5
 #define WCA_MAX_LAYERS 32      /* decoder layers of the largest published Whisper (large-v3) */
 #define WCA_MAX_MEDFILT 31     /* odd widths 1..31 */
 #define WCA_TOKENS_PER_SECOND 50.0 /* whisper.audio.TOKENS_PER_SECOND, timing.py:10,111 */
@@ -168,9 +168,11 @@ WCA_API int wca_topk_heads(const float *d_scores, const wca_utt_t *d_utts, int n
 /* (3c) Aggregation.  Replaces timing.py:86-89 ("mean") and timing.py:95-97 ("topk"):
  *   matrix[t,f] = (1/n_sel) * sum_{i<n_sel} a_i[t,f] / ||a_i[:,f]||_2 ,  heads taken in list order,
  * the column norm running over ALL T rows; rows [row_begin,row_end) are written to
- * d_matrix + matrix_off as (N, F) fp32 (timing.py:102). */
+ * d_matrix + matrix_off as (N, F) fp32 (timing.py:102).  max_sel >= 1 is an upper bound of the descriptors' n_sel (a
+ * performance hint: launches of single-head aggregations, probe_oracle.py:82-90, get a leaner kernel; the result does
+ * not depend on it). */
 WCA_API int wca_aggregate_heads(const float *d_ws, const int32_t *d_sel, const wca_utt_t *d_utts, int n_utts,
-                        int max_tokens, int max_frames, float *d_matrix, wca_stream_t stream);
+                        int max_tokens, int max_frames, int max_sel, float *d_matrix, wca_stream_t stream);
 
 /* (4) Batched DTW + backtrace + boundary extraction.  Replaces timing.py:103
  * `dtw(-matrix)` (upstream dtw_cpu + backtrace), timing.py:110-111 (jump frames) and

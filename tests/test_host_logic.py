@@ -97,7 +97,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert sorted(_cabi.EXPORTS) == names
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.wca_abi_version() == _cabi.ABI_VERSION == 4
+    assert lib.wca_abi_version() == _cabi.ABI_VERSION == 5
     assert lib.wca_capture_partials_floats(384, 45, 150) == 384 * 1 * 4 * 151 and lib.wca_capture_writes_partials(1500, 3, 0) == 1
     assert lib.wca_capture_writes_partials(1500, 9, 0) == 0 and lib.wca_capture_writes_partials(150, 3, _cabi.WCA_CAPTURE_FORCE_SIMT) == 0
     assert lib.wca_dtw_workspace_bytes(4, 445, 1500) == 0  # largest legal Whisper problem fits in smem

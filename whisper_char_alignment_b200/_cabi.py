@@ -20,7 +20,7 @@ WCA_CAPTURE_RAW_LOGITS = 1
 WCA_CAPTURE_FORCE_SIMT = 2
 WCA_CAPTURE_TRACE = 4
 WCA_MAX_LAYERS = 32
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 EXPORTS = (
     "wca_abi_version", "wca_last_error", "wca_launch_count", "wca_device_info", "wca_capture_attention", "wca_full_attention", "wca_add_layernorm", "wca_debug_enc_attn_buffer", "wca_debug_capture_trace", "wca_medfilt_softmax",
@@ -83,7 +83,7 @@ def load() -> ctypes.CDLL:
     lib.wca_medfilt_softmax.argtypes = [vp, i64, i64, i32, i32, f32, vp, vp]
     lib.wca_head_scores.argtypes = [vp, vp, i32, i32, i32, i32, f32, f32, f32, vp, vp]
     lib.wca_topk_heads.argtypes = [vp, vp, i32, i32, vp, vp, vp]
-    lib.wca_aggregate_heads.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
+    lib.wca_aggregate_heads.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
     lib.wca_dtw_workspace_bytes.restype = i64
     lib.wca_dtw_workspace_bytes.argtypes = [i32, i32, i32]
     lib.wca_dtw_align.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
@@ -342,11 +342,12 @@ def topk_heads(scores, d_utts, n_utts, n_heads, sel, sel_scores):
         )
 
 
-def aggregate_heads(ws_base: int, sel, d_utts, n_utts, max_tokens, max_frames, matrix):
+def aggregate_heads(ws_base: int, sel, d_utts, n_utts, max_tokens, max_frames, matrix, max_sel: int = 2):
+    """max_sel: an upper bound of the descriptors' n_sel (1 selects the single-head kernel of the probe sweep)."""
     with _timed("wca_aggregate_heads"):
         _check(
             load().wca_aggregate_heads(ws_base, _dev_ptr(sel, torch.int32, "sel"), _dev_ptr(d_utts), n_utts, max_tokens,
-                                       max_frames, _dev_ptr(matrix, torch.float32, "matrix"), _stream()),
+                                       max_frames, max(int(max_sel), 1), _dev_ptr(matrix, torch.float32, "matrix"), _stream()),
             "wca_aggregate_heads",
         )
 

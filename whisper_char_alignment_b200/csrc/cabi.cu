@@ -49,7 +49,7 @@ int launch_medfilt_softmax_rows(const float *, int64_t, int64_t, int, int, float
 int launch_medfilt_softmax_batched(float *, const wca_utt_t *, int, int, int, int, int, float, int, cudaStream_t);
 int launch_head_scores(const float *, const wca_utt_t *, int, int, int, float, float, float, float *, cudaStream_t);
 int launch_topk_heads(const float *, const wca_utt_t *, int, int, int32_t *, float *, cudaStream_t);
-int launch_aggregate_heads(const float *, const int32_t *, const wca_utt_t *, int, int, int, float *, cudaStream_t);
+int launch_aggregate_heads(const float *, const int32_t *, const wca_utt_t *, int, int, int, int, float *, cudaStream_t);
 int64_t dtw_workspace_bytes(int, int, int);
 int launch_dtw_align(const float *, const wca_utt_t *, int, int, int, int, int32_t *, int32_t *, int32_t *, int32_t *,
                      const int32_t *, double *, double *, void *, int64_t, cudaStream_t);
@@ -242,12 +242,12 @@ int wca_topk_heads(const float *d_scores, const wca_utt_t *d_utts, int n_utts, i
 }
 
 int wca_aggregate_heads(const float *d_ws, const int32_t *d_sel, const wca_utt_t *d_utts, int n_utts, int max_tokens,
-                        int max_frames, float *d_matrix, wca_stream_t stream) {
+                        int max_frames, int max_sel, float *d_matrix, wca_stream_t stream) {
     WCA_CHECK_ARG(d_ws && d_sel && d_utts && d_matrix, "wca_aggregate_heads: null pointer");
-    WCA_CHECK_ARG(n_utts >= 0 && n_utts <= 65535 && max_tokens >= 1 && max_frames >= 1,
+    WCA_CHECK_ARG(n_utts >= 0 && n_utts <= 65535 && max_tokens >= 1 && max_frames >= 1 && max_sel >= 1,
                   "wca_aggregate_heads: bad geometry");
     if (n_utts == 0) return WCA_OK;
-    return launch_aggregate_heads(d_ws, d_sel, d_utts, n_utts, max_tokens, max_frames, d_matrix,
+    return launch_aggregate_heads(d_ws, d_sel, d_utts, n_utts, max_tokens, max_frames, max_sel, d_matrix,
                                   static_cast<cudaStream_t>(stream));
 }
 

@@ -194,12 +194,18 @@ __global__ void __launch_bounds__(256) topk_heads_kernel(const float *__restrict
 
 // grid (ceil(max_frames/32), n_utts), block 256 = 8 warps x 32 columns, dynamic smem
 // T*32 floats of accumulators.  Lane <-> frame (128-byte coalesced rows), warp <-> rows.
+template <int kGroup>
 __global__ void __launch_bounds__(256) aggregate_heads_kernel(const float *__restrict__ ws,
                                                               const int32_t *__restrict__ sel,
                                                               const wca_utt_t *__restrict__ utts,
                                                               float *__restrict__ matrix) {
     extern __shared__ float acc_s[];  // [T][32]
-    __shared__ float part[2][8][kWarp];
+    // Heads are taken kGroup at a time: their loads are in flight together and the block meets once per group instead of
+    // once per head (mean aggregation walks all 384 / 640 heads: one head per barrier was a chain of ~1 us round trips,
+    // 6 % of the HBM rate).  The heads of a group are still added in selection order, so the sums are unchanged bit for bit.
+    // kGroup = 1 serves launches of single-head aggregations (the probe sweep: thousands of small blocks, where the 48
+    // registers of the grouped code cost more in occupancy than they save).
+    __shared__ float part[2][kGroup][8][kWarp];
     const wca_utt_t u = utts[blockIdx.y];
     const int T = u.n_tokens, F = u.n_frames;
     const int f0 = blockIdx.x * kWarp;
@@ -210,22 +216,51 @@ __global__ void __launch_bounds__(256) aggregate_heads_kernel(const float *__res
 
     for (int t = warp; t < T; t += warps) acc_s[t * kWarp + lane] = 0.f;
 
-    for (int i = 0; i < u.n_sel; ++i) {
-        const float *a = ws + u.ws_off + (int64_t)sel[u.sel_off + i] * T * F;
-        float ss = 0.f;
+    int buf = 0;
+    for (int i0 = 0; i0 < u.n_sel; i0 += kGroup, buf ^= 1) {
+        const float *a[kGroup];
+        float ss[kGroup];
+#pragma unroll
+        for (int g = 0; g < kGroup; ++g) {
+            const int i = min(i0 + g, u.n_sel - 1);  // past the end: a valid pointer that is never loaded from
+            a[g] = ws + u.ws_off + (int64_t)sel[u.sel_off + i] * T * F + f;
+            ss[g] = 0.f;
+        }
+        const int ng = min(kGroup, u.n_sel - i0);  // single-head aggregations (the probe sweep) must not load four times
         if (live)
             for (int t = warp; t < T; t += warps) {
-                const float p = a[(int64_t)t * F + f];
-                ss = fmaf(p, p, ss);
-            }
-        part[i & 1][warp][lane] = ss;
-        __syncthreads();
-        float tot = 0.f;
+                float p[kGroup];
 #pragma unroll
-        for (int w = 0; w < 8; ++w) tot += (w < warps) ? part[i & 1][w][lane] : 0.f;
-        const float cn = sqrtf(tot);  // ||a_i[:, f]||_2 over all T rows (timing.py:86 / :96)
+                for (int g = 0; g < kGroup; ++g) p[g] = g < ng ? a[g][(int64_t)t * F] : 0.f;
+#pragma unroll
+                for (int g = 0; g < kGroup; ++g) ss[g] = fmaf(p[g], p[g], ss[g]);
+            }
+#pragma unroll
+        for (int g = 0; g < kGroup; ++g)
+            if (g < ng) part[buf][g][warp][lane] = ss[g];
+        __syncthreads();
+        float cn[kGroup];
+#pragma unroll
+        for (int g = 0; g < kGroup; ++g) {
+            cn[g] = 1.f;
+            if (g < ng) {  // (block-uniform)
+                float tot = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) tot += (w < warps) ? part[buf][g][w][lane] : 0.f;
+                cn[g] = sqrtf(tot);  // ||a_i[:, f]||_2 over all T rows (timing.py:86 / :96)
+            }
+        }
         if (live)
-            for (int t = warp; t < T; t += warps) acc_s[t * kWarp + lane] += a[(int64_t)t * F + f] / cn;
+            for (int t = warp; t < T; t += warps) {
+                float p[kGroup];
+#pragma unroll
+                for (int g = 0; g < kGroup; ++g) p[g] = g < ng ? a[g][(int64_t)t * F] : 0.f;
+                float acc = acc_s[t * kWarp + lane];
+#pragma unroll
+                for (int g = 0; g < kGroup; ++g)
+                    if (g < ng) acc += p[g] / cn[g];
+                acc_s[t * kWarp + lane] = acc;
+            }
     }
 
     // rows are accumulated by warp (t % warps) but written out by warp ((t - row_begin) % warps)
@@ -261,7 +296,7 @@ int launch_topk_heads(const float *d_scores, const wca_utt_t *d_utts, int n_utts
 }
 
 int launch_aggregate_heads(const float *d_ws, const int32_t *d_sel, const wca_utt_t *d_utts, int n_utts,
-                           int max_tokens, int max_frames, float *d_matrix, cudaStream_t stream) {
+                           int max_tokens, int max_frames, int max_sel, float *d_matrix, cudaStream_t stream) {
     const size_t smem = (size_t)max_tokens * kWarp * sizeof(float);
     if (smem > 200u * 1024u) {
         set_error("wca_aggregate_heads: max_tokens=%d exceeds the shared-memory accumulator", max_tokens);
@@ -269,10 +304,17 @@ int launch_aggregate_heads(const float *d_ws, const int32_t *d_sel, const wca_ut
     }
     // the 48 KB a kernel gets without opting in cover static + dynamic shared memory: this kernel has 2 KB of static
     // partials, so 369-384 token rows (46-48 KB of accumulators) already need the attribute
-    if (smem > 40u * 1024u)
-        WCA_CUDA(cudaFuncSetAttribute(aggregate_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // (8 KB of static partials in the grouped instantiation)
     const dim3 grid((max_frames + kWarp - 1) / kWarp, n_utts);
-    aggregate_heads_kernel<<<grid, 256, smem, stream>>>(d_ws, d_sel, d_utts, d_matrix);
+    if (max_sel <= 1) {
+        if (smem > 40u * 1024u)
+            WCA_CUDA(cudaFuncSetAttribute(aggregate_heads_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        aggregate_heads_kernel<1><<<grid, 256, smem, stream>>>(d_ws, d_sel, d_utts, d_matrix);
+    } else {
+        if (smem > 32u * 1024u)
+            WCA_CUDA(cudaFuncSetAttribute(aggregate_heads_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        aggregate_heads_kernel<4><<<grid, 256, smem, stream>>>(d_ws, d_sel, d_utts, d_matrix);
+    }
     {
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) {

@@ -377,7 +377,8 @@ def force_align_batch(ws_list, tokens_list, tokenizer, aligned_unit_type="subwor
             n = int(r["row_end"] - r["row_begin"]) * int(r["n_frames"])
             matrix[int(r["matrix_off"]): int(r["matrix_off"]) + n].copy_(m[0, 0, int(r["row_begin"]): int(r["row_end"])].reshape(-1))
     else:
-        _cabi.aggregate_heads(plan.base_ptr, sel, plan.d_utts, B, plan.max_tokens, plan.max_frames, matrix)
+        _cabi.aggregate_heads(plan.base_ptr, sel, plan.d_utts, B, plan.max_tokens, plan.max_frames, matrix,
+                              max_sel=int(plan.recs["n_sel"].max()))
 
     wb_flat = np.concatenate([
         np.pad(wb, (0, wc + 1 - len(wb))) if len(wb) < wc + 1 else wb[: wc + 1] for wb, wc in zip(wb_all, word_counts)
@@ -498,7 +499,7 @@ def _align_single_heads(ws_list, head_lists, tokens_list, tokenizer, aligned_uni
     sel = torch.zeros(P, dtype=torch.int32, device=dev)
     matrix = torch.empty(max(int((n_rows * rep(F)).sum()), 1), dtype=torch.float32, device=dev)
     max_tokens, max_frames, max_rows = int(T.max()), int(F.max()), int(n_rows.max())
-    _cabi.aggregate_heads(base_ptr, sel, d_utts, P, max_tokens, max_frames, matrix)
+    _cabi.aggregate_heads(base_ptr, sel, d_utts, P, max_tokens, max_frames, matrix, max_sel=1)
     d_wb = torch.from_numpy(np.concatenate([np.tile(wb_all[b], int(n_heads[b])) for b in range(B)]).astype(np.int32)).to(dev, non_blocking=True)
     times = torch.empty(2, int((rep(n_words) + 1).sum()), dtype=torch.float64, device=dev)
     trace_bytes = _cabi.dtw_workspace_bytes(P, max_rows, max_frames)
