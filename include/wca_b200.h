@@ -122,6 +122,13 @@ WCA_API int wca_full_attention(const float *d_q, const float *d_k, const float *
                        int n_kv, int n_heads, int head_dim, int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_out,
                        wca_stream_t stream);
 
+/* (1b') The same kernel with the causal mask of the decoder's self-attention (upstream whisper/model.py
+ * TextDecoder: `mask = triu(-inf, 1)`, qkv_attention(..., mask)): key j is visible to query i only for j <= i.
+ * Same layout and arithmetic as wca_full_attention; key blocks past a tile's last query row are not visited. */
+WCA_API int wca_causal_attention(const float *d_q, const float *d_k, const float *d_v, float *d_out, int n_batch, int n_q,
+                         int n_kv, int n_heads, int head_dim, int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_out,
+                         wca_stream_t stream);
+
 /* (1c) Residual add + LayerNorm of the same forward (upstream ResidualAttentionBlock: `x = x + f(ln(x))`,
  * whisper/model.py LayerNorm = fp32 torch layer_norm): y = x + h (skipped when d_h is NULL; written when d_y is
  * not NULL), n = (y - mean(y)) / sqrt(var(y) + eps) * gamma + beta per row, biased variance, fp32.  All

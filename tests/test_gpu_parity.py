@@ -438,6 +438,30 @@ def test_cross_attention_output_matches_fp64_reference(shape, dev):
     assert err <= 3e-6 * max(1.0, ref.abs().max().item()), err
 
 
+@pytest.mark.parametrize("shape", [(1, 1, 1), (3, 45, 16), (2, 63, 2), (2, 64, 6), (2, 65, 6), (2, 130, 8), (1, 200, 3),
+                                   (2, 448, 20)], ids=str)
+def test_causal_attention_matches_fp64_reference(shape, dev):
+    """wca_causal_attention (the decoder's self-attention: upstream TextDecoder mask = triu(-inf, 1)) against torch fp64:
+    rows that see one key, the diagonal inside / at the edge of 64-key blocks, several 128-row query tiles (key blocks
+    past a tile's last row are skipped), a strided (fused qkv) input and large logits growing with the key index
+    (lazy rescale on the diagonal blocks)."""
+    from whisper_char_alignment_b200 import _cabi
+
+    B, T, H = shape
+    g = torch.Generator(device=dev).manual_seed(T * 17 + H)
+    fused = torch.randn(B, T, 3 * H * 64, device=dev, generator=g)
+    q, k, v = fused[..., : H * 64], fused[..., H * 64: 2 * H * 64], fused[..., 2 * H * 64:]
+    if T >= 130:  # logits that grow along the keys on one head: the running reference has to move
+        k[:, :, :64] = q[:, :1, :64] * torch.linspace(0.0, 3.0, T, device=dev)[None, :, None]
+    out = _cabi.full_attention(q, k, v, H, causal=True)
+    sp = lambda t: t.double().view(B, T, H, 64).transpose(1, 2)  # noqa: E731
+    logits = sp(q) @ sp(k).transpose(-1, -2) / 8.0
+    logits = logits + torch.full((T, T), float("-inf"), device=dev, dtype=torch.float64).triu(1)
+    ref = (torch.softmax(logits, dim=-1) @ sp(v)).transpose(1, 2).reshape(B, T, H * 64)
+    err = (out.double() - ref).abs().max().item()
+    assert err <= 3e-6 * max(1.0, ref.abs().max().item()), err
+
+
 def test_encoder_attention_large_logits_and_lazy_rescale(dev):
     """Peaky rows (|logit| ~ 100) and rows whose logits grow monotonically with the key index:
     the second forces the lazy rescale of the running reference on every few blocks."""

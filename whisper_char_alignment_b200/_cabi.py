@@ -23,7 +23,7 @@ WCA_MAX_LAYERS = 32
 ABI_VERSION = 5
 
 EXPORTS = (
-    "wca_abi_version", "wca_last_error", "wca_launch_count", "wca_device_info", "wca_capture_attention", "wca_full_attention", "wca_add_layernorm", "wca_debug_enc_attn_buffer", "wca_debug_capture_trace", "wca_medfilt_softmax",
+    "wca_abi_version", "wca_last_error", "wca_launch_count", "wca_device_info", "wca_capture_attention", "wca_full_attention", "wca_causal_attention", "wca_add_layernorm", "wca_debug_enc_attn_buffer", "wca_debug_capture_trace", "wca_medfilt_softmax",
     "wca_head_scores", "wca_head_scores_from_partials", "wca_capture_writes_partials", "wca_capture_partials_floats", "wca_topk_heads", "wca_aggregate_heads", "wca_dtw_workspace_bytes", "wca_dtw_align",
 )
 
@@ -79,6 +79,7 @@ def load() -> ctypes.CDLL:
     lib.wca_capture_partials_floats.argtypes = [i32, i32, i32]
     lib.wca_head_scores_from_partials.argtypes = [vp, vp, i32, i32, f32, f32, vp, vp]
     lib.wca_full_attention.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, vp]
+    lib.wca_causal_attention.argtypes = lib.wca_full_attention.argtypes
     lib.wca_add_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, f32, vp]
     lib.wca_medfilt_softmax.argtypes = [vp, i64, i64, i32, i32, f32, vp, vp]
     lib.wca_head_scores.argtypes = [vp, vp, i32, i32, i32, i32, f32, f32, f32, vp, vp]
@@ -263,9 +264,11 @@ def head_scores_from_partials(partials: torch.Tensor, d_utts, n_utts, n_heads, w
         )
 
 
-def full_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_heads: int, out: torch.Tensor | None = None):
+def full_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_heads: int, out: torch.Tensor | None = None,
+                   causal: bool = False):
     """q: (batch, n_q, n_heads*64), k, v: (batch, n_kv, n_heads*64), fp32, last dim contiguous, rows evenly
-    strided.  Returns softmax(q k^T / 8) v as (batch, n_q, n_heads*64) (wca_full_attention)."""
+    strided.  Returns softmax(q k^T / 8) v as (batch, n_q, n_heads*64) (wca_full_attention); causal=True masks the
+    keys j > i of query i (wca_causal_attention: the decoder's self-attention)."""
     batch, n_q, width = q.shape
     n_kv = k.shape[1]
     for t, name, rows in ((q, "q", n_q), (k, "k", n_kv), (v, "v", n_kv)):
@@ -275,12 +278,13 @@ def full_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_heads: i
             raise WcaError(f"full_attention: {name} must be (batch, rows, width) with contiguous rows")
     if out is None:
         out = torch.empty(batch, n_q, width, dtype=torch.float32, device=q.device)
-    with _timed("wca_full_attention"):
+    name = "wca_causal_attention" if causal else "wca_full_attention"
+    with _timed(name):
         _check(
-            load().wca_full_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), _dev_ptr(out, torch.float32, "out"),
-                                      batch, n_q, n_kv, n_heads, width // n_heads, q.stride(1), k.stride(1), v.stride(1),
-                                      out.stride(1), _stream()),
-            "wca_full_attention",
+            getattr(load(), name)(q.data_ptr(), k.data_ptr(), v.data_ptr(), _dev_ptr(out, torch.float32, "out"), batch, n_q,
+                                  n_kv, n_heads, width // n_heads, q.stride(1), k.stride(1), v.stride(1), out.stride(1),
+                                  _stream()),
+            name,
         )
     return out
 

@@ -55,7 +55,7 @@ int launch_dtw_align(const float *, const wca_utt_t *, int, int, int, int, int32
                      const int32_t *, double *, double *, void *, int64_t, cudaStream_t);
 
 int launch_full_attention(const float *, const float *, const float *, float *, int, int, int, int, int64_t, int64_t, int64_t,
-                          int64_t, cudaStream_t);
+                          int64_t, int, cudaStream_t);
 
 void set_enc_attn_debug_buffer(float *);
 int launch_add_layernorm(const float *, const float *, const float *, const float *, float *, float *, int64_t, int, float,
@@ -133,33 +133,47 @@ int wca_capture_attention(const float *const *h_q_layers, const float *const *h_
                                           medfilt_width, qk_scale, sms, st);
 }
 
-int wca_full_attention(const float *d_q, const float *d_k, const float *d_v, float *d_out, int n_batch, int n_q, int n_kv,
-                       int n_heads, int head_dim, int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_out,
-                       wca_stream_t stream) {
-    WCA_CHECK_ARG(d_q && d_k && d_v && d_out, "wca_full_attention: null pointer");
+static int attention_entry(const char *who, const float *d_q, const float *d_k, const float *d_v, float *d_out, int n_batch,
+                           int n_q, int n_kv, int n_heads, int head_dim, int64_t ld_q, int64_t ld_k, int64_t ld_v,
+                           int64_t ld_out, int causal, wca_stream_t stream) {
+    WCA_CHECK_ARG(d_q && d_k && d_v && d_out, "%s: null pointer", who);
     if (head_dim != kHeadDim) {
-        set_error("wca_full_attention: head_dim=%d unsupported (every Whisper size uses 64)", head_dim);
+        set_error("%s: head_dim=%d unsupported (every Whisper size uses 64)", who, head_dim);
         return WCA_ERR_UNSUPPORTED;
     }
     WCA_CHECK_ARG(n_batch >= 0 && n_batch <= 65535 && n_heads >= 1 && n_heads <= 65535 && n_q >= 1 && n_q < (1 << 24) &&
                       n_kv >= 1 && n_kv < (1 << 24),
-                  "wca_full_attention: bad geometry (batch %d, n_q %d, n_kv %d, heads %d)", n_batch, n_q, n_kv, n_heads);
+                  "%s: bad geometry (batch %d, n_q %d, n_kv %d, heads %d)", who, n_batch, n_q, n_kv, n_heads);
     const int64_t width = (int64_t)n_heads * head_dim;
     WCA_CHECK_ARG(ld_q >= width && ld_k >= width && ld_v >= width && ld_out >= width && ld_q % 4 == 0 && ld_k % 4 == 0 &&
                       ld_v % 4 == 0 && ld_out % 4 == 0,
-                  "wca_full_attention: leading dimensions must cover H*Dh=%lld and be multiples of 4", (long long)width);
+                  "%s: leading dimensions must cover H*Dh=%lld and be multiples of 4", who, (long long)width);
     WCA_CHECK_ARG(((uintptr_t)d_q | (uintptr_t)d_k | (uintptr_t)d_v | (uintptr_t)d_out) % 16 == 0,
-                  "wca_full_attention: pointers must be 16-byte aligned");
+                  "%s: pointers must be 16-byte aligned", who);
     if (n_batch == 0) return WCA_OK;
     int cc = 0;
     int rc = device_sm_count(nullptr, &cc);
     if (rc) return rc;
     if (cc < 100) {
-        set_error("wca_full_attention: needs compute capability 10.x (tcgen05), device is %d", cc);
+        set_error("%s: needs compute capability 10.x (tcgen05), device is %d", who, cc);
         return WCA_ERR_NO_DEVICE;
     }
-    return launch_full_attention(d_q, d_k, d_v, d_out, n_batch, n_q, n_kv, n_heads, ld_q, ld_k, ld_v, ld_out,
+    return launch_full_attention(d_q, d_k, d_v, d_out, n_batch, n_q, n_kv, n_heads, ld_q, ld_k, ld_v, ld_out, causal,
                                  static_cast<cudaStream_t>(stream));
+}
+
+int wca_full_attention(const float *d_q, const float *d_k, const float *d_v, float *d_out, int n_batch, int n_q, int n_kv,
+                       int n_heads, int head_dim, int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_out,
+                       wca_stream_t stream) {
+    return attention_entry("wca_full_attention", d_q, d_k, d_v, d_out, n_batch, n_q, n_kv, n_heads, head_dim, ld_q, ld_k, ld_v,
+                           ld_out, 0, stream);
+}
+
+int wca_causal_attention(const float *d_q, const float *d_k, const float *d_v, float *d_out, int n_batch, int n_q, int n_kv,
+                         int n_heads, int head_dim, int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_out,
+                         wca_stream_t stream) {
+    return attention_entry("wca_causal_attention", d_q, d_k, d_v, d_out, n_batch, n_q, n_kv, n_heads, head_dim, ld_q, ld_k,
+                           ld_v, ld_out, 1, stream);
 }
 
 int wca_add_layernorm(const float *d_x, const float *d_h, const float *d_gamma, const float *d_beta, float *d_y, float *d_n,

@@ -1,4 +1,4 @@
-// tcgen05 / TMEM / TMA unmasked attention (the Whisper audio encoder's self-attention and the decoder's
+// tcgen05 / TMEM / TMA attention, unmasked or causal (the Whisper audio encoder's self-attention, the decoder's
 // cross-attention OUTPUT), fp32 in / fp32-grade out.
 //
 // Row a2 of the scope table (the teacher-forced forward, reference timing.py:57-58): the
@@ -113,6 +113,7 @@ struct Args {
     float *out;
     int64_t ld_out;
     int n_q, n_ctx;    // query rows and key/value rows per batch item
+    int causal;        // key j is visible to query i only for j <= i (the decoder's self-attention)
     float scale_log2;  // Dh^-1/2 * log2(e)
     unsigned skip;     // debug only (env WCA_EA_SKIP): 2 P V MMAs, 4 Q K^T MMAs, 8 operand split
     float *dbg;        // debug only (wca_debug_enc_attn_buffer): CTA (0,0,0) dumps S of block 0, raw O, l, m
@@ -123,7 +124,8 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * kQRows, head = blockIdx.y, batch = blockIdx.z;
     const int col0 = head * kHeadDim;
-    const int n_blocks = (a.n_ctx + kKeys - 1) / kKeys;
+    // causal: the key blocks past the tile's last query row are never visited
+    const int n_blocks = ((a.causal ? min(a.n_ctx, q0 + kQRows) : a.n_ctx) + kKeys - 1) / kKeys;
     const uint32_t bars = smem_u32(smem + kOffBar);
     auto bar = [&](int which) { return bars + 8u * (uint32_t)which; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kOffTmem);
@@ -336,7 +338,9 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
         float m_ref = 0.f, l_sum = 0.f;
         for (int j = 0; j < n_blocks; ++j) {
             const int b = j % kSBufs;
-            const int n_valid = min(kKeys, a.n_ctx - j * kKeys);  // < 64 only for the last block
+            const int n_block = min(kKeys, a.n_ctx - j * kKeys);  // < 64 only for the last block
+            // keys of this block the thread's query row may see (causal: up to its own position; <= 0: none)
+            const int n_valid = a.causal ? min(n_block, q0 + row + 1 - j * kKeys) : n_block;
             mbar_wait(bar(kSFull + b), (j / kSBufs) & 1);
             tc_fence_after();
             stamp(a.dbg, tr, kEvSFull, j);
@@ -365,7 +369,9 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_kernel(const __grid_cons
                 m_ref = mx * c;
             }
             const float neg_m = -m_ref;
-            const bool full = n_valid == kKeys;  // only the last block of a context that is not a multiple of 64 is ragged
+            // warp-uniform: every row of the tile sees all 64 keys (ragged: the last block of a context that is not a
+            // multiple of 64; causal: the blocks the diagonal of this tile runs through)
+            const bool full = n_block == kKeys && (!a.causal || j * kKeys + kKeys - 1 <= q0);
             if (full) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -563,7 +569,7 @@ static float *g_enc_attn_dbg = nullptr;
 void set_enc_attn_debug_buffer(float *d_buf) { g_enc_attn_dbg = d_buf; }
 
 int launch_full_attention(const float *d_q, const float *d_k, const float *d_v, float *d_out, int n_batch, int n_q, int n_ctx,
-                          int n_heads, int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_out, cudaStream_t stream) {
+                          int n_heads, int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_out, int causal, cudaStream_t stream) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
@@ -589,6 +595,7 @@ int launch_full_attention(const float *d_q, const float *d_k, const float *d_v, 
     a.ld_out = ld_out;
     a.n_q = n_q;
     a.n_ctx = n_ctx;
+    a.causal = causal;
     a.dbg = g_enc_attn_dbg;
     {
         static int skip = -1;

@@ -6,9 +6,10 @@ the published architecture and the published parameter names: a checkpoint's
 `model_state_dict` (or the oracle's seeded random init) loads with `load_state_dict`.
 Differences from the upstream module that matter for this path:
 
-  * attention always runs through `scaled_dot_product_attention`; the encoder never
-    materialises its 1500x1500 maps (the reference's `disable_sdpa()` wraps the whole
-    forward, timing.py:57-58, and pays for 24 x 144 MB of encoder maps nobody reads);
+  * attention never materialises its maps (the reference's `disable_sdpa()` wraps the whole
+    forward, timing.py:57-58, and pays for 24 x 144 MB of encoder maps nobody reads): on a GPU
+    the encoder self-attention, the cross-attention output and the causal decoder self-attention
+    run on the sm_100a kernel of csrc/enc_attn.cu, otherwise on `scaled_dot_product_attention`;
   * cross-attention logits are NOT produced here.  `timing.get_attentions` taps the
     outputs of `cross_attn.query` / `cross_attn.key` and hands them to the sm_100a
     capture kernel, so any module with this tree (including a stock upstream model)
@@ -56,8 +57,10 @@ def dims_for(name: str) -> ModelDimensions:
 
 
 #: "wca": unmasked attention (encoder self-attention, decoder cross-attention output) runs on csrc/enc_attn.cu;
-#: "sdpa": torch SDPA (fp32 CUDA-core kernel).  The decoder's causal self-attention always stays on SDPA.
+#: "sdpa": torch SDPA (fp32 CUDA-core kernel).
 ENCODER_ATTENTION = os.environ.get("WCA_ENCODER_ATTENTION", "wca")
+#: "wca": the decoder's causal self-attention runs on the same kernel (wca_causal_attention); "sdpa": torch SDPA
+CAUSAL_ATTENTION = os.environ.get("WCA_CAUSAL_ATTENTION", "wca")
 
 
 class _Norm(nn.LayerNorm):
@@ -139,14 +142,14 @@ class Attention(nn.Module):
             q, k, v = self.query(x), self.key(src), self.value(src)
         if tap is not None:
             tap.append((q, k))
-        if (not causal and ENCODER_ATTENTION == "wca" and q.is_cuda and q.dtype == torch.float32
-                and q.shape[-1] == 64 * self.n_head):
-            # unmasked attention (encoder self-attention, decoder cross-attention output): the sm_100a
+        if (ENCODER_ATTENTION == "wca" and q.is_cuda and q.dtype == torch.float32 and q.shape[-1] == 64 * self.n_head
+                and (not causal or CAUSAL_ATTENTION == "wca")):
+            # encoder self-attention, decoder cross-attention output and (causal) decoder self-attention: the sm_100a
             # tcgen05 kernel (csrc/enc_attn.cu) reads the projection outputs in place (no head split /
             # transposes) and keeps fp32 accuracy with 3 x tf32 products
             from . import _cabi
 
-            return self.out(_cabi.full_attention(q, k, v, self.n_head)), None
+            return self.out(_cabi.full_attention(q, k, v, self.n_head, causal=causal and q.shape[1] > 1)), None
         q, k, v = self._split(q), self._split(k), self._split(v)  # views, also of the column slices of a fused projection
         # SDPA's default scale is d_head^-1/2 == (d_head^-1/4)^2, the published scaling
         ctx = F.scaled_dot_product_attention(q, k, v, is_causal=causal and q.shape[2] > 1)
